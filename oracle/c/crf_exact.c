@@ -1,0 +1,254 @@
+/* Plain-C restatement of the CTC-CRF decode arithmetic -- the bit-exact checker for the CUDA decode.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): built by oracle/c/Makefile into
+ * oracle/_build/libxb_oracle.so and loaded by tests/, smoke() and bench.py's cpu_baseline leg.
+ *
+ * Follows (paths relative to /root/reference/ub-bonito/):
+ *   bonito/crf/model.py:26-36    CTC_CRF.idx                       -> src_state()
+ *   bonito/crf/model.py:41-46    CTC_CRF.logZ (alpha_0 = beta_T = 0) -> xbo_crf_alpha / xbo_crf_logz
+ *   bonito/crf/model.py:92-95    CTC_CRF.viterbi (posteriors(Max).argmax % NZ) -> xbo_crf_viterbi
+ *   bonito/crf/model.py:215-218  SeqdistModel.decode_batch (posteriors + 1e-8, log, viterbi, int16, T)
+ *   bonito/crf/model.py:97-100   CTC_CRF.path_to_str                -> xbo_pack
+ *   bonito/crf/basecall.py:56-76 left-packed (N,T) int8 sequence / qstring
+ * and the seqdist semiring algebra restated in oracle/seqdist_restated.py (Log: logsumexp / softmax,
+ * Max: max / one-hot at first arg-max; edge marginal = (M + alpha[idx]) + beta).
+ *
+ * Arithmetic contract shared with xna_basecaller_b200/csrc/crf_decode.cu (all fp32, round to nearest,
+ * no contraction; exp/log from xb_exact_math.h):
+ *   logsumexp over the NZ edges of a state:  m = max_k x_k;  s = (..(e_0 + e_1) + ..) + e_{NZ-1},
+ *       e_k = exp(x_k - m);  result = m + log(s).   Backward (beta) edge order: stay, then moves j = 0..n-1.
+ *   softmax over all C*NZ edges of a step: gmax = max; e = exp(x - gmax); per state s_c = sum_k e (k order);
+ *       S = tree_sum(s_c) (below); p = e * (1 / S);  lp = log(p + 1e-8).
+ *   tree_sum over states: state c sits in lane c%32 of warp c/32 (missing lanes contribute +0); each warp
+ *       does the xor-butterfly v_i += v_{i^off}, off = 16,8,4,2,1; warp totals are added in warp order.
+ *   arg-max over the flat edge index c*NZ+k: strictly greater wins, i.e. first index on ties.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../xna_basecaller_b200/csrc/xb_exact_math.h"
+
+#define MAXC 1296
+#define MAXNZ 8
+
+typedef struct {
+    int n, sl, C, NZ, n_pow;   /* n_pow = n^(sl-1) */
+} lattice;
+
+static int lattice_init(lattice *L, int n_base, int state_len) {
+    L->n = n_base; L->sl = state_len; L->NZ = n_base + 1;
+    int C = 1, p = 1;
+    for (int i = 0; i < state_len; i++) { C *= n_base; if (i < state_len - 1) p *= n_base; }
+    L->C = C; L->n_pow = p;
+    return (C <= MAXC && L->NZ <= MAXNZ && n_base >= 2) ? 0 : -1;
+}
+
+/* source state of edge k entering state c (crf/model.py:31-36) */
+static inline int src_state(const lattice *L, int c, int k) {
+    return k == 0 ? c : (k - 1) * L->n_pow + c / L->n;
+}
+
+static float tree_sum(const float *v, int C) {
+    float total = 0.0f;
+    int W = (C + 31) / 32;
+    for (int w = 0; w < W; w++) {
+        float a[32], b[32];
+        for (int i = 0; i < 32; i++) { int c = w * 32 + i; a[i] = c < C ? v[c] : 0.0f; }
+        for (int off = 16; off >= 1; off >>= 1) {
+            for (int i = 0; i < 32; i++) b[i] = XB_ADD(a[i], a[i ^ off]);
+            memcpy(a, b, sizeof a);
+        }
+        total = (w == 0) ? a[0] : XB_ADD(total, a[0]);
+    }
+    return total;
+}
+
+static inline float lse_finish(float m, float s) { return XB_ADD(m, xb_logf(s)); }
+
+/* alpha_{t+1}[c] from alpha_t and the scores of step t */
+static void alpha_step(const lattice *L, const float *M, const float *a, float *out, int use_max) {
+    for (int c = 0; c < L->C; c++) {
+        float x[MAXNZ], m = 0.0f;
+        for (int k = 0; k < L->NZ; k++) {
+            x[k] = XB_ADD(M[c * L->NZ + k], a[src_state(L, c, k)]);
+            m = (k == 0 || x[k] > m) ? x[k] : m;
+        }
+        if (use_max) { out[c] = m; continue; }
+        float s = 0.0f;
+        for (int k = 0; k < L->NZ; k++) {
+            float e = xb_expf(XB_SUB(x[k], m));
+            s = (k == 0) ? e : XB_ADD(s, e);
+        }
+        out[c] = lse_finish(m, s);
+    }
+}
+
+/* beta_t[c'] from beta_{t+1} and the scores of step t; edges leaving c': stay (c',0) then the moves
+ * into c = (c' % n_pow)*n + j through edge k = 1 + c'/n_pow, j = 0..n-1 */
+static void beta_step(const lattice *L, const float *M, const float *b, float *out, int use_max) {
+    for (int cp = 0; cp < L->C; cp++) {
+        float x[MAXNZ], m;
+        x[0] = XB_ADD(M[cp * L->NZ], b[cp]);
+        m = x[0];
+        int k = 1 + cp / L->n_pow, base = (cp % L->n_pow) * L->n;
+        for (int j = 0; j < L->n; j++) {
+            int c = base + j;
+            x[1 + j] = XB_ADD(M[c * L->NZ + k], b[c]);
+            m = x[1 + j] > m ? x[1 + j] : m;
+        }
+        if (use_max) { out[cp] = m; continue; }
+        float s = 0.0f;
+        for (int j = 0; j < L->NZ; j++) {
+            float e = xb_expf(XB_SUB(x[j], m));
+            s = (j == 0) ? e : XB_ADD(s, e);
+        }
+        out[cp] = lse_finish(m, s);
+    }
+}
+
+int xbo_crf_alpha(const float *scores, int T, int N, int n_base, int state_len, float *alpha) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    size_t S = (size_t)L.C * L.NZ;
+    for (int n = 0; n < N; n++) {
+        for (int c = 0; c < L.C; c++) alpha[(size_t)n * L.C + c] = 0.0f;
+        for (int t = 0; t < T; t++)
+            alpha_step(&L, scores + ((size_t)t * N + n) * S, alpha + ((size_t)t * N + n) * L.C,
+                       alpha + ((size_t)(t + 1) * N + n) * L.C, 0);
+    }
+    return 0;
+}
+
+int xbo_crf_logz(const float *scores, int T, int N, int n_base, int state_len, float *logz) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    size_t S = (size_t)L.C * L.NZ;
+    for (int n = 0; n < N; n++) {
+        float a[2][MAXC];
+        for (int c = 0; c < L.C; c++) a[0][c] = 0.0f;
+        for (int t = 0; t < T; t++) alpha_step(&L, scores + ((size_t)t * N + n) * S, a[t & 1], a[(t + 1) & 1], 0);
+        const float *aT = a[T & 1];
+        float m = aT[0], e[MAXC];
+        for (int c = 1; c < L.C; c++) m = aT[c] > m ? aT[c] : m;
+        for (int c = 0; c < L.C; c++) e[c] = xb_expf(XB_SUB(aT[c], m));
+        logz[n] = lse_finish(m, tree_sum(e, L.C));
+    }
+    return 0;
+}
+
+/* Max-semiring forward sweep + arg-max against stored bmax (T+1, C) of ONE sequence (stride C). */
+static void viterbi_forward(const lattice *L, const float *lp, size_t lp_stride, const float *bmax, int T,
+                            int8_t *labels) {
+    float am[2][MAXC];
+    for (int c = 0; c < L->C; c++) am[0][c] = 0.0f;
+    for (int t = 0; t < T; t++) {
+        const float *M = lp + (size_t)t * lp_stride, *a = am[t & 1], *b = bmax + (size_t)(t + 1) * L->C;
+        float *an = am[(t + 1) & 1];
+        float best = 0.0f; int besti = -1;
+        for (int c = 0; c < L->C; c++) {
+            float m = 0.0f;
+            for (int k = 0; k < L->NZ; k++) {
+                float v = XB_ADD(M[c * L->NZ + k], a[src_state(L, c, k)]);
+                m = (k == 0 || v > m) ? v : m;
+                float sc = XB_ADD(v, b[c]);
+                if (besti < 0 || sc > best) { best = sc; besti = c * L->NZ + k; }
+            }
+            an[c] = m;
+        }
+        labels[t] = (int8_t)(besti % L->NZ);
+    }
+}
+
+/* decode_batch: labels (N,T) int8; optional post / lp outputs (T,N,C*NZ). */
+int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len, float *post, float *lp_out,
+                   int8_t *labels) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    size_t S = (size_t)L.C * L.NZ;
+    float *alpha = (float *)malloc((size_t)(T + 1) * L.C * sizeof(float));
+    float *bmax = (float *)malloc((size_t)(T + 1) * L.C * sizeof(float));
+    float *lp = (float *)malloc((size_t)T * S * sizeof(float));
+    float *x = (float *)malloc(S * sizeof(float));
+    float *sc = (float *)malloc(L.C * sizeof(float));
+    if (!alpha || !bmax || !lp || !x || !sc) return -2;
+    for (int n = 0; n < N; n++) {
+        for (int c = 0; c < L.C; c++) alpha[c] = 0.0f;
+        for (int t = 0; t < T; t++)
+            alpha_step(&L, scores + ((size_t)t * N + n) * S, alpha + (size_t)t * L.C, alpha + (size_t)(t + 1) * L.C, 0);
+        float beta[2][MAXC];
+        for (int c = 0; c < L.C; c++) { beta[T & 1][c] = 0.0f; bmax[(size_t)T * L.C + c] = 0.0f; }
+        for (int t = T - 1; t >= 0; t--) {
+            const float *M = scores + ((size_t)t * N + n) * S, *a = alpha + (size_t)t * L.C;
+            const float *b1 = beta[(t + 1) & 1];
+            float gmax = 0.0f;
+            for (int c = 0; c < L.C; c++)
+                for (int k = 0; k < L.NZ; k++) {
+                    float v = XB_ADD(XB_ADD(M[c * L.NZ + k], a[src_state(&L, c, k)]), b1[c]);
+                    x[c * L.NZ + k] = v;
+                    gmax = (c == 0 && k == 0) || v > gmax ? v : gmax;
+                }
+            for (int c = 0; c < L.C; c++) {
+                float s = 0.0f;
+                for (int k = 0; k < L.NZ; k++) {
+                    float e = xb_expf(XB_SUB(x[c * L.NZ + k], gmax));
+                    x[c * L.NZ + k] = e;
+                    s = (k == 0) ? e : XB_ADD(s, e);
+                }
+                sc[c] = s;
+            }
+            float inv = XB_RCP(tree_sum(sc, L.C));
+            float *lpt = lp + (size_t)t * S;
+            for (size_t i = 0; i < S; i++) {
+                float p = XB_MUL(x[i], inv);
+                if (post) post[((size_t)t * N + n) * S + i] = p;
+                lpt[i] = xb_logf(XB_ADD(p, XB_POST_EPS));
+            }
+            if (lp_out) memcpy(lp_out + ((size_t)t * N + n) * S, lpt, S * sizeof(float));
+            beta_step(&L, M, b1, beta[t & 1], 0);
+            beta_step(&L, lpt, bmax + (size_t)(t + 1) * L.C, bmax + (size_t)t * L.C, 1);
+        }
+        viterbi_forward(&L, lp, S, bmax, T, labels + (size_t)n * T);
+    }
+    free(alpha); free(bmax); free(lp); free(x); free(sc);
+    return 0;
+}
+
+int xbo_crf_posteriors(const float *scores, int T, int N, int n_base, int state_len, float *post) {
+    int8_t *lab = (int8_t *)malloc((size_t)N * T);
+    if (!lab) return -2;
+    int rc = xbo_crf_decode(scores, T, N, n_base, state_len, post, NULL, lab);
+    free(lab);
+    return rc;
+}
+
+/* CTC_CRF.viterbi on arbitrary scores: labels (N,T) int8 */
+int xbo_crf_viterbi(const float *scores, int T, int N, int n_base, int state_len, int8_t *labels) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    size_t S = (size_t)L.C * L.NZ;
+    float *bmax = (float *)malloc((size_t)(T + 1) * L.C * sizeof(float));
+    if (!bmax) return -2;
+    for (int n = 0; n < N; n++) {
+        for (int c = 0; c < L.C; c++) bmax[(size_t)T * L.C + c] = 0.0f;
+        for (int t = T - 1; t >= 0; t--)
+            beta_step(&L, scores + ((size_t)t * N + n) * S, bmax + (size_t)(t + 1) * L.C, bmax + (size_t)t * L.C, 1);
+        viterbi_forward(&L, scores + (size_t)n * S, (size_t)N * S, bmax, T, labels + (size_t)n * T);
+    }
+    free(bmax);
+    return 0;
+}
+
+/* path_to_str + left-pack: seq/qstring (N,T) int8 zero padded, lens (N) */
+int xbo_pack(const int8_t *labels, int N, int T, const char *alphabet, int8_t *seq, int8_t *qstring, int32_t *lens) {
+    for (int n = 0; n < N; n++) {
+        int len = 0;
+        memset(seq + (size_t)n * T, 0, T);
+        memset(qstring + (size_t)n * T, 0, T);
+        for (int t = 0; t < T; t++) {
+            int l = labels[(size_t)n * T + t];
+            if (l != 0) { seq[(size_t)n * T + len] = (int8_t)alphabet[l]; qstring[(size_t)n * T + len] = 'O'; len++; }
+        }
+        lens[n] = len;
+    }
+    return 0;
+}
+
+void xbo_expf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_expf(x[i]); }
+void xbo_logf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_logf(x[i]); }

@@ -1,0 +1,117 @@
+"""ctypes front-end of oracle/c/crf_exact.c (the bit-exact CPU checker for the CUDA decode).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, '_build', 'libxb_oracle.so')
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, 'c', 'crf_exact.c')
+    hdr = os.path.join(_HERE, '..', 'xna_basecaller_b200', 'csrc', 'xb_exact_math.h')
+    stale = (not os.path.exists(_SO)
+             or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)))
+    if force or stale:
+        subprocess.check_call(['make', '-s', '-B', '-C', os.path.join(_HERE, 'c')])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _dims(n_base, state_len):
+    return n_base ** state_len, n_base + 1
+
+
+def expf(x):
+    x = _f32(x)
+    y = np.empty_like(x)
+    lib().xbo_expf_array(_p(x), _p(y), ctypes.c_long(x.size))
+    return y
+
+
+def logf(x):
+    x = _f32(x)
+    y = np.empty_like(x)
+    lib().xbo_logf_array(_p(x), _p(y), ctypes.c_long(x.size))
+    return y
+
+
+def crf_alpha(scores, n_base, state_len=3):
+    s = _f32(scores)
+    T, N, _ = s.shape
+    C, _ = _dims(n_base, state_len)
+    out = np.empty((T + 1, N, C), dtype=np.float32)
+    assert lib().xbo_crf_alpha(_p(s), T, N, n_base, state_len, _p(out)) == 0
+    return out
+
+
+def crf_logz(scores, n_base, state_len=3):
+    s = _f32(scores)
+    T, N, _ = s.shape
+    out = np.empty(N, dtype=np.float32)
+    assert lib().xbo_crf_logz(_p(s), T, N, n_base, state_len, _p(out)) == 0
+    return out
+
+
+def crf_decode(scores, n_base, state_len=3, want_post=False, want_lp=False):
+    """labels (N,T) int8 [, posteriors (T,N,C*NZ)] [, log(post+1e-8) (T,N,C*NZ)]."""
+    s = _f32(scores)
+    T, N, _ = s.shape
+    labels = np.empty((N, T), dtype=np.int8)
+    post = np.empty_like(s) if want_post else None
+    lp = np.empty_like(s) if want_lp else None
+    rc = lib().xbo_crf_decode(_p(s), T, N, n_base, state_len,
+                              _p(post) if want_post else None, _p(lp) if want_lp else None, _p(labels))
+    assert rc == 0
+    out = [labels]
+    if want_post:
+        out.append(post)
+    if want_lp:
+        out.append(lp)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def crf_viterbi(scores, n_base, state_len=3):
+    s = _f32(scores)
+    T, N, _ = s.shape
+    labels = np.empty((N, T), dtype=np.int8)
+    assert lib().xbo_crf_viterbi(_p(s), T, N, n_base, state_len, _p(labels)) == 0
+    return labels
+
+
+def pack(labels, alphabet):
+    """path_to_str + left-pack: sequence (N,T) int8, qstring (N,T) int8, lens (N,) int32."""
+    lab = np.ascontiguousarray(labels, dtype=np.int8)
+    N, T = lab.shape
+    seq = np.empty((N, T), dtype=np.int8)
+    qs = np.empty((N, T), dtype=np.int8)
+    lens = np.empty(N, dtype=np.int32)
+    abc = ''.join(alphabet).encode()
+    assert lib().xbo_pack(_p(lab), N, T, ctypes.c_char_p(abc), _p(seq), _p(qs), _p(lens)) == 0
+    return seq, qs, lens
+
+
+def strings(labels, alphabet):
+    seq, _, lens = pack(labels, alphabet)
+    return [seq[i, :lens[i]].astype('u1').tobytes().decode() for i in range(len(lens))]

@@ -1,0 +1,136 @@
+"""Generate tests/golden/*.npz by running the REAL reference code (build container only).
+
+    python tests/golden/make_golden.py
+
+Everything here executes /root/reference/ub-bonito/bonito/{nn,util,crf/model,crf/basecall}.py
+through ``oracle.refshim`` (the only stand-ins are the absent third-party modules: seqdist is
+``oracle.seqdist_restated``, koi.decode.to_str is restated).  Inputs are NOT stored: tests
+regenerate them from the seeds below (numpy RandomState / torch.Generator on CPU are stable
+for a fixed build), so the fixtures stay small.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refshim, bonito_oracle as bo  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ALPHABETS = {4: ['N', 'A', 'C', 'G', 'T'], 5: ['N', 'A', 'C', 'G', 'T', 'X'],
+             6: ['N', 'A', 'C', 'G', 'T', 'X', 'Y']}
+
+
+def synthetic_scores(seed, T, N, n_base, state_len=3, blank=2.0):
+    """SURVEY 8c golden (ii) / config 3: non-blank ~U(-5,5), blank column constant."""
+    rs = np.random.RandomState(seed)
+    C = n_base ** state_len
+    s = rs.uniform(-5, 5, size=(T, N, C, n_base + 1)).astype(np.float32)
+    s[..., 0] = blank
+    return torch.from_numpy(s.reshape(T, N, -1))
+
+
+def synthetic_targets(seed, N, n_base, lo, hi):
+    rs = np.random.RandomState(seed)
+    lengths = rs.randint(lo, hi + 1, size=N)
+    tg = np.zeros((N, hi), dtype=np.int64)
+    for i, l in enumerate(lengths):
+        tg[i, :l] = rs.randint(1, n_base + 1, size=l)
+    return torch.from_numpy(tg), torch.from_numpy(lengths.astype(np.int64))
+
+
+def synthetic_signal(seed, N, L):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(N, 1, L, generator=g)
+
+
+def main():
+    mods = refshim.install()
+    RM, RU, RB = mods['bonito.crf.model'], mods['bonito.util'], mods['bonito.crf.basecall']
+
+    # ---- (i)+(ii) CRF: reference CTC_CRF methods on synthetic scores
+    crf = {}
+    for n_base, alphabet in ALPHABETS.items():
+        sd = RM.CTC_CRF(3, alphabet)
+        for seed in (0, 1):
+            T, N = 160, 3
+            s = synthetic_scores(seed, T, N, n_base)
+            key = 'n%d_s%d_' % (n_base, seed)
+            post = sd.posteriors(s)
+            crf[key + 'logZ'] = sd.logZ(s).numpy()
+            crf[key + 'post_sub'] = post[::9, :, ::7].numpy()
+            crf[key + 'post_rowsum'] = post.sum(2).numpy()
+            lp = (post + 1e-8).log()
+            crf[key + 'paths'] = sd.viterbi(lp).numpy().astype(np.int8)
+            crf[key + 'paths_raw'] = sd.viterbi(s).numpy().astype(np.int8)
+            model = RM.SeqdistModel(torch.nn.Identity(), sd)
+            crf[key + 'strings'] = np.array(model.decode_batch(s))
+            tg, tl = synthetic_targets(100 + seed, N, n_base, 30, 50)
+            crf[key + 'ctc_loss'] = sd.ctc_loss(s, tg, tl, reduction='none').numpy()
+            crf[key + 'alpha_last'] = sd.forward_scores(s)[-1].numpy()
+            crf[key + 'beta_first'] = sd.backward_scores(s)[0].numpy()
+    np.savez_compressed(os.path.join(OUT, 'crf.npz'), **crf)
+
+    # ---- (iii) encoder: reference Model with deterministic weights
+    enc = {}
+    for n_base in (5, 6):
+        cfg = refshim.reference_config(ALPHABETS[n_base])
+        model = RM.Model(cfg).eval()
+        sd = bo.reference_state_dict(n_base=n_base, seed=11)
+        model.load_state_dict(sd)
+        x = synthetic_signal(21, 2, 500)
+        with torch.no_grad():
+            stem = model.encoder[2](model.encoder[1](model.encoder[0](x)))
+            l1 = model.encoder[4](stem.permute(2, 0, 1))
+            scores = model(x)
+        key = 'n%d_' % n_base
+        enc[key + 'stem_sub'] = stem[:, ::16, :].numpy()
+        enc[key + 'lstm1_sub'] = l1[:, :, ::16].numpy()
+        enc[key + 'scores'] = scores.numpy()
+        enc[key + 'strings'] = np.array(model.decode_batch(scores))
+        cs = RB.compute_scores(model, x)
+        enc[key + 'cs_sequence'] = cs['sequence'].numpy()
+        enc[key + 'cs_qstring'] = cs['qstring'].numpy()
+        enc[key + 'cs_moves'] = np.asarray(cs['moves'])
+    np.savez_compressed(os.path.join(OUT, 'encoder.npz'), **enc)
+
+    # ---- (iv) chunk / stitch on index arrays
+    st = {}
+    for cs_, ov in ((4000, 500), (3600, 500), (1000, 100)):
+        for L in (cs_ - 1, cs_, cs_ + 1, 7500, 10000, 10001, 2 * cs_ - ov, 19999):
+            sig = torch.arange(L, dtype=torch.float32)
+            ch = RU.chunk(sig, cs_, ov)
+            key = 'c%d_o%d_L%d_' % (cs_, ov, L)
+            st[key + 'first'] = ch[:, 0, 0].numpy().astype(np.int64)       # start sample of each chunk
+            st[key + 'lastrow'] = ch[-1, 0, -3:].numpy().astype(np.int64)
+            T = cs_ // 5
+            lab = torch.arange(ch.shape[0] * T, dtype=torch.int32).reshape(ch.shape[0], T)
+            st[key + 'stitched'] = RU.stitch(lab, cs_, ov, L, 5).numpy()
+            st[key + 'stitched_rev'] = RU.stitch(lab, cs_, ov, L, 5, reverse=True).numpy()
+    np.savez_compressed(os.path.join(OUT, 'stitch.npz'), **st)
+
+    # ---- end to end: reference basecall() on a few short reads (CPU, fp32)
+    class Read:
+        def __init__(self, rid, sig):
+            self.read_id, self.signal = rid, sig
+
+    cfg = refshim.reference_config(ALPHABETS[5])
+    model = RM.Model(cfg).eval()
+    model.load_state_dict(bo.reference_state_dict(n_base=5, seed=11))
+    rs = np.random.RandomState(77)
+    lengths = [700, 1000, 1001, 2350, 1900, 3100]
+    reads = [Read('read%d' % i, rs.randn(L).astype(np.float32)) for i, L in enumerate(lengths)]
+    e2e = {'lengths': np.array(lengths)}
+    for rd, res in RB.basecall(model, reads, chunksize=1000, overlap=100, batchsize=4):
+        e2e[rd.read_id + '_sequence'] = np.array(res['sequence'])
+        e2e[rd.read_id + '_qstring'] = np.array(res['qstring'])
+        e2e[rd.read_id + '_sig_move_len'] = np.array(len(res['sig_move']))
+    np.savez_compressed(os.path.join(OUT, 'basecall.npz'), **e2e)
+    for f in ('crf.npz', 'encoder.npz', 'stitch.npz', 'basecall.npz'):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()
