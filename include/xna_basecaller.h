@@ -1,0 +1,144 @@
+/* xna_basecaller.h -- C ABI of the B200-native ub-bonito basecalling forward path.
+ *
+ * One shared library (xna_basecaller_b200/libxna_b200.so), extern "C", plain pointers and sizes, no
+ * torch / C++ types.  The reference (CSB5/XNA_Basecaller, ub-bonito) is 100% Python and has no FFI of
+ * its own for this path; each entry point below replaces the reference Python symbol cited next to it
+ * (paths relative to ub-bonito/bonito/), and INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add.  The Python package xna_basecaller_b200 mirrors the reference's plugin surface
+ * (nn.py / crf/model.py / crf/basecall.py / util.py) on top of exactly these calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative xb_status otherwise; xb_last_error(h) gives the
+ *     text (h may be NULL for errors raised before a handle exists).  Nothing throws, nothing exits.
+ *   - a handle is bound to one CUDA device; it owns repacked weights and workspace, all allocated in
+ *     xb_create / xb_load_weights.  The caller owns every input/output buffer.  A handle is not
+ *     thread-safe; distinct handles are independent.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it with no host
+ *     synchronisation, except the *_host entry points, which synchronise before returning.
+ *   - device pointers unless the parameter name ends in _host.
+ *   - T = L / stride (stride 5), C = n_base^state_len states, NZ = n_base+1 edges per state,
+ *     scores are (T, N, C*NZ) fp32 in the reference's layout (nn.py:122-129).
+ *   - the 16-bit activation / weight type is fp16 (what the reference itself uses on GPU,
+ *     util.py:360-363) unless XB_FLAG_BF16 is given; accumulation and LSTM cell state are fp32.
+ */
+#ifndef XNA_BASECALLER_H
+#define XNA_BASECALLER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB_ABI_VERSION 1
+
+typedef struct xb_handle xb_handle;
+
+enum xb_status {
+    XB_OK = 0,
+    XB_ERR_ARG = -1,        /* bad argument (shape, alignment, null pointer)              */
+    XB_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed                         */
+    XB_ERR_STATE = -3,      /* call order (e.g. encoder before xb_load_weights)            */
+    XB_ERR_UNSUPPORTED = -4,/* alphabet / state_len / feature size without a compiled kernel */
+    XB_ERR_NOMEM = -5
+};
+
+enum xb_flags {
+    XB_FLAG_BF16 = 1,            /* 16-bit type is bfloat16 instead of float16                 */
+    XB_FLAG_NO_ENCODER = 2,      /* decode-only handle: no encoder workspace is allocated      */
+    XB_FLAG_LSTM_STEPWISE = 4    /* force the one-launch-per-step LSTM (debug / comparison)   */
+};
+
+enum xb_signal_dtype { XB_SIG_F32 = 0, XB_SIG_F16 = 1, XB_SIG_I16 = 2 };
+
+/* Number of weight tensors xb_load_weights expects: the reference state_dict in key order
+ * (SURVEY.md section 5): encoder.{0,1,2}.conv.{weight,bias}, encoder.{4..8}.rnn.{weight_ih_l0,
+ * weight_hh_l0,bias_ih_l0,bias_hh_l0}, encoder.9.linear.{weight,bias}. */
+#define XB_NUM_WEIGHTS 28
+
+int xb_abi_version(void);
+const char *xb_last_error(const xb_handle *h);
+
+/* Handle life cycle.  alphabet: n_base+1 letters, blank first ("NACGTX").  Replaces the state the
+ * reference keeps in Model / CTC_CRF objects (crf/model.py:24-36, 224-237). */
+int xb_create(xb_handle **out, int device, int max_N, int max_T, int n_base, int state_len,
+              const char *alphabet, int flags);
+int xb_destroy(xb_handle *h);
+
+/* util.load_model's load_state_dict (util.py:324-366): 28 fp32 device tensors in reference layout,
+ * repacked here into kernel layouts (gate-interleaved LSTM rows, K-major 16-bit GEMM operands).
+ * scale / blank_score / expand_blanks are LinearCRFEncoder's (nn.py:90-96). */
+int xb_load_weights(xb_handle *h, const float *const *tensors, int n_tensors, float scale,
+                    float blank_score, int expand_blanks, void *stream);
+
+/* nn.Convolution x3 + nn.Permute([2,0,1]) (nn.py:57-68,156-167; crf/model.py:148-151).
+ * signal (N, L) of sig_dtype -> out (T, N, 768) 16-bit. */
+int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, void *out_tnc,
+                     void *stream);
+
+/* nn.LSTM / RNNWrapper.forward (nn.py:176-235), layer in 0..4 (= encoder.4 .. encoder.8);
+ * x, y (T, N, 768) 16-bit; reverse walks time backwards by indexing (no flips). */
+int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, int N, int reverse,
+                void *stream);
+
+/* the five layers with the reference's directions reverse,fwd,reverse,fwd,reverse (crf/model.py:152-154);
+ * x is overwritten (ping-pong with handle workspace); result in y. */
+int xb_lstm_stack_fwd(xb_handle *h, void *x_tnc, void *y_tnc, int T, int N, void *stream);
+
+/* nn.LinearCRFEncoder.forward (nn.py:112-133): x (T,N,768) 16-bit -> scores (T,N,C*NZ) fp32 (or
+ * (T,N,C*n_base) when expand_blanks was 0). */
+int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, void *stream);
+
+/* Model.forward (crf/model.py:212-213): signal (N, L) -> scores (T, N, C*NZ) fp32. */
+int xb_encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores,
+                   void *stream);
+
+/* CTC_CRF.logZ (crf/model.py:41-46), Log semiring: logz (N). */
+int xb_crf_logz(xb_handle *h, const float *scores, int T, int N, float *logz, void *stream);
+
+/* CTC_CRF.forward_scores / backward_scores (crf/model.py:51-61), Log semiring: (T+1, N, C). */
+int xb_crf_forward_scores(xb_handle *h, const float *scores, int T, int N, float *alpha, void *stream);
+int xb_crf_backward_scores(xb_handle *h, const float *scores, int T, int N, float *beta, void *stream);
+
+/* SequenceDist.posteriors(scores, Log) (crf/model.py:216): post (T, N, C*NZ) fp32. */
+int xb_crf_posteriors(xb_handle *h, const float *scores, int T, int N, float *post, void *stream);
+
+/* CTC_CRF.viterbi (crf/model.py:92-95): labels (N, T) int8 in 0..n_base (already transposed). */
+int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labels_nt, void *stream);
+
+/* SeqdistModel.decode_batch (crf/model.py:215-218) + the left-packing of compute_scores
+ * (crf/basecall.py:56-76): seq / qstring (N, T) int8 zero padded (ascii letters / 'O'), lens (N).
+ * qstring, labels_nt, post may be NULL. */
+int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring,
+                  int32_t *lens, int8_t *labels_nt, float *post, void *stream);
+
+/* CTC_CRF.ctc_loss(reduction='none') forward (crf/model.py:118-131): targets (N, Lmax) int32 1-based
+ * 0-padded, lengths (N) int32 -> loss (N) fp32 = -logz / length.  normalise as in the reference. */
+int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets,
+                        int Lmax, const int32_t *lengths, int normalise, float *loss, void *stream);
+
+/* util.stitch over left-packed chunks (util.py:169-188; crf/basecall.py:15-24): for each read r,
+ * concatenates slices of its chunks' packed rows.  chunk_first[r], chunk_count[r], read_len[r]
+ * (samples) describe the reads; rows are (n_chunks_total, T) int8; out is (n_reads, out_stride) int8,
+ * out_len (n_reads). */
+int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first,
+              const int32_t *chunk_count, const int32_t *read_len, int n_reads, int chunksize,
+              int overlap, int stride, int8_t *out, int out_stride, int32_t *out_len, void *stream);
+
+/* crf.basecall.compute_scores end to end with HOST buffers (crf/basecall.py:27-82): H2D of the
+ * chunk batch, encoder, decode, D2H of the packed sequences; synchronises.  signal_host (N, L) fp32,
+ * seq_host (N, T) int8, lens_host (N).  Pinned host memory makes the copies asynchronous. */
+int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L, int8_t *seq_host,
+                           int32_t *lens_host, void *stream);
+
+/* Introspection used by tests / bench: number of kernels this library launched on the handle so far. */
+int64_t xb_launch_count(const xb_handle *h);
+
+/* Standalone tensor-core GEMM self-test hook: D (M,N) fp32 = A (M,K) x B (N,K)^T, 16-bit operands. */
+int xb_gemm_selftest(xb_handle *h, const void *A, const void *B, float *D, int M, int N, int K,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XNA_BASECALLER_H */

@@ -1,0 +1,176 @@
+"""GPU parity tests of the CUDA CRF decode against the oracle (through the C ABI).
+
+Bar: labels / packed strings bit-exact against oracle/c/crf_exact.c and against the golden vectors
+produced by the reference's own CTC_CRF code; posteriors / logZ / alpha / beta within fp32 tolerances
+(the reference's torch.logsumexp / softmax association order is not reproducible bit for bit)."""
+import numpy as np
+import pytest
+import torch
+
+from make_golden import ALPHABETS, synthetic_scores, synthetic_targets
+from oracle import bonito_oracle as bo
+from oracle import cexact
+
+pytestmark = pytest.mark.gpu
+
+POST_TOL = 2e-5      # max abs error on posteriors (values in [0,1]) against the torch restatement
+LOGZ_RTOL = 2e-6     # relative error on logZ (|logZ| ~ 1e3 at T=160: fp32 ulp 6e-5)
+
+
+@pytest.fixture(scope='module')
+def handles():
+    from xna_basecaller_b200._lib import Handle
+    hs = {n: Handle(ALPHABETS[n], 3, max_N=64, max_T=800, encoder=False) for n in (4, 5, 6)}
+    yield hs
+    for h in hs.values():
+        h.close()
+
+
+@pytest.mark.parametrize('n_base', [4, 5, 6])
+@pytest.mark.parametrize('seed', [0, 1])
+def test_decode_matches_reference_golden(handles, golden, n_base, seed):
+    h = handles[n_base]
+    g = golden['crf']
+    key = 'n%d_s%d_' % (n_base, seed)
+    s = synthetic_scores(seed, 160, 3, n_base)
+    seq, qs, lens, labels, post = h.decode(s, want_labels=True, want_post=True)
+    torch.cuda.synchronize()
+    labels = labels.cpu().numpy()
+    assert np.array_equal(labels.T, g[key + 'paths'])                       # bit-exact Viterbi paths
+    strings = [bytes(seq[i, :lens[i]].cpu().numpy().astype('u1')).decode() for i in range(3)]
+    assert strings == list(g[key + 'strings'])                              # decode_batch strings
+    assert np.array_equal((qs.cpu().numpy() != 0), (seq.cpu().numpy() != 0))
+    assert set(np.unique(qs.cpu().numpy())) <= {0, ord('O')}
+    post = post.cpu().numpy()
+    assert np.abs(post[::9, :, ::7] - g[key + 'post_sub']).max() < POST_TOL
+    assert np.abs(post.sum(2) - 1).max() < 1e-5
+    lz = h.logZ(s).cpu().numpy()
+    np.testing.assert_allclose(lz, g[key + 'logZ'], rtol=LOGZ_RTOL)
+    np.testing.assert_allclose(h.forward_scores(s)[-1].cpu().numpy(), g[key + 'alpha_last'], rtol=LOGZ_RTOL, atol=1e-4)
+    np.testing.assert_allclose(h.backward_scores(s)[0].cpu().numpy(), g[key + 'beta_first'], rtol=LOGZ_RTOL, atol=1e-4)
+    raw = h.viterbi(s).cpu().numpy()
+    assert np.array_equal(raw.T, g[key + 'paths_raw'])                      # CTC_CRF.viterbi on raw scores
+
+
+@pytest.mark.parametrize('n_base,T,N', [(5, 800, 64), (6, 800, 32), (4, 333, 17), (5, 1, 3), (5, 2, 1)])
+def test_decode_bit_exact_vs_c_oracle(handles, n_base, T, N):
+    h = handles[n_base]
+    s = synthetic_scores(1000 + T + N, T, N, n_base)
+    seq, qs, lens, labels, post = h.decode(s, want_labels=True, want_post=True)
+    torch.cuda.synchronize()
+    o_labels, o_post, o_lp = cexact.crf_decode(s.numpy(), n_base, want_post=True, want_lp=True)
+    assert np.array_equal(labels.cpu().numpy(), o_labels)
+    # posteriors are produced by the same arithmetic contract: bit-equal, not just close
+    assert np.array_equal(post.cpu().numpy().view(np.uint32), o_post.view(np.uint32))
+    o_seq, o_qs, o_lens = cexact.pack(o_labels, ALPHABETS[n_base])
+    assert np.array_equal(seq.cpu().numpy(), o_seq)
+    assert np.array_equal(qs.cpu().numpy(), o_qs)
+    assert np.array_equal(lens.cpu().numpy(), o_lens)
+    assert np.array_equal(h.logZ(s).cpu().numpy().view(np.uint32), cexact.crf_logz(s.numpy(), n_base).view(np.uint32))
+    assert np.array_equal(h.viterbi(s).cpu().numpy(), cexact.crf_viterbi(s.numpy(), n_base))
+    assert np.array_equal(h.forward_scores(s).cpu().numpy().view(np.uint32),
+                          cexact.crf_alpha(s.numpy(), n_base).view(np.uint32))
+
+
+def test_decode_saturated_ties(handles):
+    """5*tanh saturates: many exactly equal scores.  First-index tie-breaking must match."""
+    n_base = 5
+    h = handles[n_base]
+    rs = np.random.RandomState(3)
+    s = rs.choice(np.array([-5.0, 5.0, 2.0, 0.0], dtype=np.float32), size=(200, 8, 125, 6))
+    s[..., 0] = 2.0
+    s = torch.from_numpy(s.reshape(200, 8, -1))
+    labels = h.decode(s, want_labels=True)[3].cpu().numpy()
+    assert np.array_equal(labels, cexact.crf_decode(s.numpy(), n_base))
+    assert np.array_equal(h.viterbi(s).cpu().numpy(), cexact.crf_viterbi(s.numpy(), n_base))
+
+
+def test_decode_all_blank_is_empty(handles):
+    """Random-init models give every non-blank score < blank: decode must be the empty string."""
+    h = handles[5]
+    s = torch.full((100, 4, 125, 6), -1.0)
+    s[..., 0] = 2.0
+    seq, qs, lens = h.decode(s.reshape(100, 4, -1))
+    assert lens.cpu().tolist() == [0, 0, 0, 0]
+    assert int(seq.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('n_base', [5, 6])
+def test_posteriors_vs_torch_restatement(handles, n_base):
+    h = handles[n_base]
+    s = synthetic_scores(77, 120, 4, n_base)
+    ref = bo.CRF(3, ALPHABETS[n_base]).posteriors(s)
+    got = h.posteriors(s).cpu()
+    assert (got - ref).abs().max().item() < POST_TOL
+
+
+@pytest.mark.parametrize('n_base', [4, 5, 6])
+def test_ctc_loss_matches_reference_golden(handles, golden, n_base):
+    h = handles[n_base]
+    g = golden['crf']
+    for seed in (0, 1):
+        s = synthetic_scores(seed, 160, 3, n_base)
+        tg, tl = synthetic_targets(100 + seed, 3, n_base, 30, 50)
+        loss = h.ctc_loss(s, tg, tl).cpu().numpy()
+        np.testing.assert_allclose(loss, g['n%d_s%d_ctc_loss' % (n_base, seed)], rtol=2e-5)
+
+
+def test_ctc_loss_long_targets(handles):
+    n_base = 5
+    h = handles[n_base]
+    s = synthetic_scores(5, 800, 6, n_base)
+    tg, tl = synthetic_targets(9, 6, n_base, 350, 450)
+    ref = bo.CRF(3, ALPHABETS[n_base]).ctc_loss(s, tg, tl, reduction='none')
+    np.testing.assert_allclose(h.ctc_loss(s, tg, tl).cpu().numpy(), ref.numpy(), rtol=5e-5)
+
+
+def test_stitch_matches_reference_golden(handles, golden):
+    h = handles[5]
+    g = golden['stitch']
+    for cs, ov in ((4000, 500), (3600, 500), (1000, 100)):
+        T = cs // 5
+        lens, firsts, counts, rows, expect = [], [], [], [], []
+        for L in (cs - 1, cs, cs + 1, 7500, 10000, 10001, 2 * cs - ov, 19999):
+            key = 'c%d_o%d_L%d_' % (cs, ov, L)
+            nch = len(g[key + 'first'])
+            # rows hold 1 + (flat index % 120) so that every position is a distinct-ish non-zero byte
+            lab = (np.arange(nch * T).reshape(nch, T) % 120 + 1).astype(np.int8)
+            firsts.append(sum(counts))
+            counts.append(nch)
+            lens.append(L)
+            rows.append(lab)
+            expect.append((g[key + 'stitched'] % 120 + 1).astype(np.int8))
+        out, out_len = h.stitch(torch.from_numpy(np.concatenate(rows)), firsts, counts, lens, cs, ov)
+        out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+        for i, e in enumerate(expect):
+            assert out_len[i] == len(e)
+            assert np.array_equal(out[i, :len(e)], e)
+
+
+def test_full_size_properties():
+    """BASELINE configs 2 and 3 sizes: properties that do not need the oracle at full size, plus an
+    oracle spot check on a few sequences cut out of the big batch (chunks are independent)."""
+    from xna_basecaller_b200._lib import Handle
+    for n_base, N in ((5, 512), (6, 1024)):
+        h = Handle(ALPHABETS[n_base], 3, max_N=N, max_T=800, encoder=False)
+        C, NZ = n_base ** 3, n_base + 1
+        g = torch.Generator(device='cuda').manual_seed(7)
+        s = torch.empty(800, N, C, NZ, device='cuda').uniform_(-5, 5, generator=g)
+        s[..., 0] = 2.0
+        s = s.reshape(800, N, -1)
+        seq, qs, lens, labels, post = h.decode(s, want_labels=True, want_post=True)
+        torch.cuda.synchronize()
+        assert (post.sum(2) - 1).abs().max().item() < 1e-5
+        assert post.min().item() >= 0
+        assert int(labels.min()) >= 0 and int(labels.max()) <= n_base
+        assert torch.equal((labels != 0).sum(1).int(), lens)
+        # idempotence / determinism: a second run gives the same bits
+        seq2, _, lens2 = h.decode(s, want_qstring=False)
+        assert torch.equal(seq, seq2) and torch.equal(lens, lens2)
+        # batch independence + oracle: first, middle and last sequences
+        pick = [0, N // 2 + 1, N - 1]
+        sub = s[:, pick].contiguous().cpu().numpy()
+        assert np.array_equal(labels[pick].cpu().numpy(), cexact.crf_decode(sub, n_base))
+        del s, post
+        h.close()
+        torch.cuda.empty_cache()

@@ -1,0 +1,132 @@
+"""GPU parity tests of the CUDA encoder (conv stem, LSTM stack, CRF head) against the fp32 oracle and the
+golden vectors produced by the reference's own bonito.nn / bonito.crf.model code.
+
+Tolerance (BASELINE.json north_star): max abs error <= 1e-2 on the CRF scores (range +-5) with 16-bit
+tensor-core operands against the fp32 reference.  The 16-bit type is fp16 by default -- what the reference
+itself runs on GPU (bonito/util.py:360-363); bf16 is an option and is checked against a looser bound."""
+import numpy as np
+import pytest
+import torch
+
+from make_golden import ALPHABETS, synthetic_signal
+from oracle import bonito_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL_F16 = 1e-2
+SCORE_TOL_BF16 = 1.5e-1
+
+
+@pytest.fixture(scope='module')
+def enc5():
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[5], 3, max_N=16, max_T=400)
+    sd = bo.reference_state_dict(n_base=5, seed=11)
+    h.load_weights(sd)
+    yield h, sd
+    h.close()
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 768), (1000, 640, 320), (77, 128, 128)])
+def test_gemm_selftest(bf16, M, N, K):
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[5], 3, max_N=4, max_T=8, bf16=bf16, encoder=False)
+    dt = torch.bfloat16 if bf16 else torch.float16
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda', generator=g).to(dt)
+    B = torch.randn(N, K, device='cuda', generator=g).to(dt)
+    D = h.gemm_selftest(A, B)
+    ref = A.float() @ B.float().t()
+    err = (D - ref).abs().max().item()
+    assert err < 1e-2 * (K / 64) ** 0.5, err
+    h.close()
+
+
+def test_conv_stem(enc5, golden):
+    h, sd = enc5
+    x = synthetic_signal(21, 2, 500)
+    got = h.conv_stem(x.cuda()).float().cpu()             # (T, N, 768)
+    ref = bo.conv_stem(sd, x).permute(2, 0, 1)
+    err = (got - ref).abs()
+    assert (err / (1 + ref.abs())).max().item() < 4e-3
+    gold = torch.from_numpy(golden['encoder']['n5_stem_sub'])       # reference code output (N, 48, T)
+    assert ((got.permute(1, 2, 0)[:, ::16, :] - gold).abs() / (1 + gold.abs())).max().item() < 4e-3
+
+
+@pytest.mark.parametrize('reverse', [True, False])
+def test_lstm_layer(enc5, reverse):
+    h, sd = enc5
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(60, 5, 768, generator=g) * 0.5).half()
+    p = 'encoder.4.rnn.'
+    ref = bo.lstm_layer(x.float(), sd[p + 'weight_ih_l0'], sd[p + 'weight_hh_l0'], sd[p + 'bias_ih_l0'],
+                        sd[p + 'bias_hh_l0'], reverse)
+    got = h.lstm(0, x.cuda(), reverse).float().cpu()
+    assert (got - ref).abs().max().item() < 4e-3
+
+
+def test_lstm_first_layer_golden(enc5, golden):
+    """encoder.4 of the reference Model on the reference stem output."""
+    h, sd = enc5
+    x = synthetic_signal(21, 2, 500)
+    stem = h.conv_stem(x.cuda())
+    got = h.lstm(0, stem, True).float().cpu()
+    gold = torch.from_numpy(golden['encoder']['n5_lstm1_sub'])      # (T, N, 48)
+    assert (got[:, :, ::16] - gold).abs().max().item() < 5e-3
+
+
+def test_crf_head(enc5):
+    h, sd = enc5
+    g = torch.Generator().manual_seed(6)
+    x = (torch.rand(50, 3, 768, generator=g) * 2 - 1).half()
+    ref = bo.crf_head(sd, x.float(), 5)
+    got = h.crf_head(x.cuda()).cpu()
+    assert got.shape == ref.shape
+    assert torch.equal(got.view(50, 3, 125, 6)[..., 0], torch.full((50, 3, 125), 2.0))
+    assert (got - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize('n_base', [5, 6])
+def test_encoder_scores_vs_reference_golden(golden, n_base):
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[n_base], 3, max_N=8, max_T=200)
+    sd = bo.reference_state_dict(n_base=n_base, seed=11)
+    h.load_weights(sd)
+    x = synthetic_signal(21, 2, 500)
+    got = h.encoder(x.cuda()).cpu()
+    gold = torch.from_numpy(golden['encoder']['n%d_scores' % n_base])
+    assert got.shape == gold.shape
+    err = (got - gold).abs().max().item()
+    assert err <= SCORE_TOL_F16, err
+    # decoded strings from the CUDA scores equal the reference's decode of its own fp32 scores
+    seq, _, lens = h.decode(got, want_qstring=False)
+    strings = [bytes(seq[i, :lens[i]].cpu().numpy().astype('u1')).decode() for i in range(2)]
+    assert strings == list(golden['encoder']['n%d_strings' % n_base])
+    h.close()
+
+
+def test_encoder_bf16_option():
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[5], 3, max_N=8, max_T=200, bf16=True)
+    sd = bo.reference_state_dict(n_base=5, seed=11)
+    h.load_weights(sd)
+    x = synthetic_signal(22, 3, 500)
+    got = h.encoder(x.cuda()).cpu()
+    ref = bo.encoder_forward(sd, x, 5)
+    err = (got - ref).abs().max().item()
+    print('bf16 max abs score error', err)
+    assert err <= SCORE_TOL_BF16, err
+    h.close()
+
+
+def test_compute_scores_host_end_to_end(enc5, golden):
+    """H2D -> encoder -> decode -> D2H through the host-buffer entry point, against the reference's
+    compute_scores output (left-packed int8 rows)."""
+    h, sd = enc5
+    x = synthetic_signal(21, 2, 500)
+    seq, lens = h.compute_scores_host(x[:, 0, :].contiguous().pin_memory())
+    gold = golden['encoder']['n5_cs_sequence']
+    assert np.array_equal(seq.numpy(), gold)
+    assert lens.tolist() == [(gold[i] != 0).sum() for i in range(2)]
+    assert h.launches > 0

@@ -1,0 +1,297 @@
+"""ctypes binding of libxna_b200.so (include/xna_basecaller.h) + a thin torch-tensor front end.
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 GPU is present, every
+compute entry point raises.  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libxna_b200.so')
+
+XB_FLAG_BF16 = 1
+XB_FLAG_NO_ENCODER = 2
+XB_FLAG_LSTM_STEPWISE = 4
+XB_SIG_F32, XB_SIG_F16, XB_SIG_I16 = 0, 1, 2
+NUM_WEIGHTS = 28
+
+# every symbol include/xna_basecaller.h declares (tests check that the library exports them all)
+SYMBOLS = (
+    'xb_abi_version', 'xb_last_error', 'xb_create', 'xb_destroy', 'xb_load_weights', 'xb_conv_stem_fwd',
+    'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
+    'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
+    'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+)
+
+_lib = None
+
+
+def load():
+    """dlopen the library (works without a GPU; compute calls do not)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'xna_basecaller_b200: %s is missing -- build it with `python -m xna_basecaller_b200.build` '
+            '(there is no CPU or PyTorch fallback for this path)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.xb_abi_version.restype = ci
+    lib.xb_last_error.restype = ctypes.c_char_p
+    lib.xb_last_error.argtypes = [vp]
+    lib.xb_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ctypes.c_char_p, ci]
+    lib.xb_destroy.argtypes = [vp]
+    lib.xb_load_weights.argtypes = [vp, ctypes.POINTER(vp), ci, cf, cf, ci, vp]
+    lib.xb_conv_stem_fwd.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_lstm_fwd.argtypes = [vp, ci, vp, vp, ci, ci, ci, vp]
+    lib.xb_lstm_stack_fwd.argtypes = [vp, vp, vp, ci, ci, vp]
+    lib.xb_crf_head_fwd.argtypes = [vp, vp, vp, ci, ci, vp]
+    lib.xb_encoder_fwd.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_crf_logz.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_crf_forward_scores.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_crf_backward_scores.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_crf_posteriors.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
+    lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
+    lib.xb_compute_scores_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.xb_launch_count.restype = ctypes.c_int64
+    lib.xb_launch_count.argtypes = [vp]
+    lib.xb_gemm_selftest.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    for name in SYMBOLS:
+        if name not in ('xb_last_error', 'xb_launch_count'):
+            getattr(lib, name).restype = ci
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Handle:
+    """One xb_handle: a device, an alphabet, capacity (max_N chunks x max_T steps) and, after
+    load_weights(), the repacked encoder weights."""
+
+    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError('xna_basecaller_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = load()
+        self.alphabet = ''.join(alphabet)
+        self.n_base = len(self.alphabet) - 1
+        self.state_len = state_len
+        self.C = self.n_base ** state_len
+        self.NZ = self.n_base + 1
+        self.max_N, self.max_T = max_N, max_T
+        self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
+        self.bf16 = bf16
+        self.dtype16 = torch.bfloat16 if bf16 else torch.float16
+        flags = (XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
+        h = ctypes.c_void_p()
+        rc = self.lib.xb_create(ctypes.byref(h), self.device.index or 0, max_N, max_T, self.n_base, state_len,
+                                self.alphabet.encode(), flags)
+        if rc != 0:
+            raise RuntimeError('xb_create failed (%d): %s' % (rc, self.lib.xb_last_error(None).decode()))
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.xb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError('%s failed (%d): %s' % (what, rc, self.lib.xb_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.xb_launch_count(self.h))
+
+    # ------------------------------------------------------------------ weights / encoder
+    def load_weights(self, state_dict, scale=5.0, blank_score=2.0, expand_blanks=True):
+        """state_dict with the reference keys (encoder.0.conv.weight ... encoder.9.linear.bias)."""
+        keys = []
+        for i in range(3):
+            keys += ['encoder.%d.conv.weight' % i, 'encoder.%d.conv.bias' % i]
+        for i in range(4, 9):
+            keys += ['encoder.%d.rnn.%s' % (i, k) for k in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
+        keys += ['encoder.9.linear.weight', 'encoder.9.linear.bias']
+        tensors = [state_dict[k].detach().to(self.device, torch.float32).contiguous() for k in keys]
+        arr = (ctypes.c_void_p * NUM_WEIGHTS)(*[t.data_ptr() for t in tensors])
+        rc = self.lib.xb_load_weights(self.h, arr, NUM_WEIGHTS, float(scale),
+                                      float(blank_score if blank_score is not None else 0.0),
+                                      int(bool(expand_blanks) and blank_score is not None), _stream(self.device))
+        self._check(rc, 'xb_load_weights')
+        torch.cuda.current_stream(self.device).synchronize()   # tensors may be freed after this
+
+    def _sig(self, signal):
+        if signal.dim() == 3:
+            signal = signal[:, 0, :]
+        signal = signal.contiguous()
+        code = {torch.float32: XB_SIG_F32, torch.float16: XB_SIG_F16, torch.int16: XB_SIG_I16}.get(signal.dtype)
+        if code is None:
+            signal, code = signal.float(), XB_SIG_F32
+        return signal, code
+
+    def conv_stem(self, signal):
+        signal, code = self._sig(signal.to(self.device))
+        N, L = signal.shape
+        out = torch.empty(L // 5, N, 768, dtype=self.dtype16, device=self.device)
+        self._check(self.lib.xb_conv_stem_fwd(self.h, _ptr(signal), code, N, L, _ptr(out), _stream(self.device)),
+                    'xb_conv_stem_fwd')
+        return out
+
+    def lstm(self, layer, x, reverse):
+        x = x.contiguous()
+        T, N, _ = x.shape
+        y = torch.empty_like(x)
+        self._check(self.lib.xb_lstm_fwd(self.h, layer, _ptr(x), _ptr(y), T, N, int(reverse), _stream(self.device)),
+                    'xb_lstm_fwd')
+        return y
+
+    def lstm_stack(self, x):
+        x = x.contiguous().clone()
+        T, N, _ = x.shape
+        y = torch.empty_like(x)
+        self._check(self.lib.xb_lstm_stack_fwd(self.h, _ptr(x), _ptr(y), T, N, _stream(self.device)), 'xb_lstm_stack_fwd')
+        return y
+
+    def crf_head(self, x, expand_blanks=True):
+        x = x.contiguous()
+        T, N, _ = x.shape
+        width = self.C * self.NZ if expand_blanks else self.C * self.n_base
+        scores = torch.empty(T, N, width, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_crf_head_fwd(self.h, _ptr(x), _ptr(scores), T, N, _stream(self.device)), 'xb_crf_head_fwd')
+        return scores
+
+    def encoder(self, signal, expand_blanks=True):
+        signal, code = self._sig(signal.to(self.device))
+        N, L = signal.shape
+        width = self.C * self.NZ if expand_blanks else self.C * self.n_base
+        scores = torch.empty(L // 5, N, width, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_encoder_fwd(self.h, _ptr(signal), code, N, L, _ptr(scores), _stream(self.device)),
+                    'xb_encoder_fwd')
+        return scores
+
+    # ------------------------------------------------------------------ CRF
+    def _scores(self, scores):
+        s = scores.to(self.device, torch.float32).contiguous()
+        T, N, W = s.shape
+        if W != self.C * self.NZ:
+            raise ValueError('scores last dim %d != C*NZ = %d' % (W, self.C * self.NZ))
+        return s, T, N
+
+    def logZ(self, scores):
+        s, T, N = self._scores(scores)
+        out = torch.empty(N, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_crf_logz(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)), 'xb_crf_logz')
+        return out
+
+    def forward_scores(self, scores):
+        s, T, N = self._scores(scores)
+        out = torch.empty(T + 1, N, self.C, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_crf_forward_scores(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)),
+                    'xb_crf_forward_scores')
+        return out
+
+    def backward_scores(self, scores):
+        s, T, N = self._scores(scores)
+        out = torch.empty(T + 1, N, self.C, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_crf_backward_scores(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)),
+                    'xb_crf_backward_scores')
+        return out
+
+    def posteriors(self, scores):
+        s, T, N = self._scores(scores)
+        out = torch.empty_like(s)
+        self._check(self.lib.xb_crf_posteriors(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)), 'xb_crf_posteriors')
+        return out
+
+    def viterbi(self, scores):
+        """labels (N, T) int8."""
+        s, T, N = self._scores(scores)
+        out = torch.empty(N, T, dtype=torch.int8, device=self.device)
+        self._check(self.lib.xb_crf_viterbi(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)), 'xb_crf_viterbi')
+        return out
+
+    def decode(self, scores, want_labels=False, want_post=False, want_qstring=True):
+        """sequence (N,T) int8, qstring (N,T) int8 | None, lens (N) int32 [, labels (N,T)] [, post]."""
+        s, T, N = self._scores(scores)
+        seq = torch.empty(N, T, dtype=torch.int8, device=self.device)
+        qs = torch.empty(N, T, dtype=torch.int8, device=self.device) if want_qstring else None
+        lens = torch.empty(N, dtype=torch.int32, device=self.device)
+        labels = torch.empty(N, T, dtype=torch.int8, device=self.device) if want_labels else None
+        post = torch.empty_like(s) if want_post else None
+        self._check(self.lib.xb_crf_decode(self.h, _ptr(s), T, N, _ptr(seq), _ptr(qs), _ptr(lens), _ptr(labels),
+                                           _ptr(post), _stream(self.device)), 'xb_crf_decode')
+        out = [seq, qs, lens]
+        if want_labels:
+            out.append(labels)
+        if want_post:
+            out.append(post)
+        return tuple(out)
+
+    def ctc_loss(self, scores, targets, lengths, normalise=True):
+        s, T, N = self._scores(scores)
+        tg = targets.to(self.device, torch.int32).contiguous()
+        ln = lengths.to(self.device, torch.int32).contiguous()
+        out = torch.empty(N, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_ctc_crf_loss_fwd(self.h, _ptr(s), T, N, _ptr(tg), tg.shape[1], _ptr(ln),
+                                                 int(normalise), _ptr(out), _stream(self.device)), 'xb_ctc_crf_loss_fwd')
+        return out
+
+    def stitch(self, rows, chunk_first, chunk_count, read_len, chunksize, overlap, stride=5, out_stride=None):
+        rows = rows.to(self.device, torch.int8).contiguous()
+        T = rows.shape[1]
+        cf = torch.as_tensor(chunk_first, dtype=torch.int32, device=self.device)
+        cc = torch.as_tensor(chunk_count, dtype=torch.int32, device=self.device)
+        rl = torch.as_tensor(read_len, dtype=torch.int32, device=self.device)
+        n_reads = cf.numel()
+        if out_stride is None:
+            out_stride = int(cc.max().item()) * T
+        out = torch.zeros(n_reads, out_stride, dtype=torch.int8, device=self.device)
+        out_len = torch.empty(n_reads, dtype=torch.int32, device=self.device)
+        self._check(self.lib.xb_stitch(self.h, _ptr(rows), T, _ptr(cf), _ptr(cc), _ptr(rl), n_reads, chunksize, overlap,
+                                       stride, _ptr(out), out_stride, _ptr(out_len), _stream(self.device)), 'xb_stitch')
+        return out, out_len
+
+    def compute_scores_host(self, signal_host, seq_host=None, lens_host=None):
+        """signal_host: (N, L) fp32 CPU tensor (pinned for async copies) -> packed sequences on the host."""
+        if signal_host.dim() == 3:
+            signal_host = signal_host[:, 0, :]
+        assert signal_host.device.type == 'cpu' and signal_host.dtype == torch.float32 and signal_host.is_contiguous()
+        N, L = signal_host.shape
+        T = L // 5
+        if seq_host is None:
+            seq_host = torch.empty(N, T, dtype=torch.int8).pin_memory()
+        if lens_host is None:
+            lens_host = torch.empty(N, dtype=torch.int32).pin_memory()
+        self._check(self.lib.xb_compute_scores_host(self.h, ctypes.c_void_p(signal_host.data_ptr()), N, L,
+                                                    ctypes.c_void_p(seq_host.data_ptr()),
+                                                    ctypes.c_void_p(lens_host.data_ptr()), _stream(self.device)),
+                    'xb_compute_scores_host')
+        return seq_host, lens_host
+
+    def gemm_selftest(self, A, B):
+        A, B = A.contiguous(), B.contiguous()
+        M, K = A.shape
+        N = B.shape[0]
+        D = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_gemm_selftest(self.h, _ptr(A), _ptr(B), _ptr(D), M, N, K, _stream(self.device)),
+                    'xb_gemm_selftest')
+        return D

@@ -1,0 +1,556 @@
+// CTC-CRF scans for sm_100a: Log-semiring forward (alpha / logZ), fused backward sweep (beta, posteriors,
+// log-posteriors, Max-semiring beta) and Max-semiring forward sweep with arg-max, labels and left-packing.
+//
+// Reference semantics: bonito/crf/model.py:26-46 (idx, logZ), :51-61 (forward/backward scores), :92-100
+// (viterbi, path_to_str), :215-218 (decode_batch); bonito/crf/basecall.py:56-76 (left-packed rows); the
+// seqdist semiring algebra as restated in oracle/seqdist_restated.py.  The arithmetic contract (operation
+// order, reduction tree, exp/log) is the one written at the top of oracle/c/crf_exact.c; the two must stay
+// in lock step because the tests demand bit-equal labels.
+//
+// Mapping: one CTA per sequence, one thread per CRF state (C = n_base^state_len; 128 threads for the
+// 5-letter alphabet, 224 for 6 letters), so all N sequences are resident at once (N/148 CTAs per SM) and
+// the serial dependence over T is hidden by the other CTAs of the SM.  The score rows of a sequence are
+// streamed through a cp.async ring in shared memory several steps ahead of the recurrence (HBM-bound
+// part); state vectors ping-pong in shared memory with one barrier per step.
+#include "xb_common.cuh"
+#include "xb_exact_math.h"
+
+namespace {
+
+template <int NB, int SL> struct Lat {
+    static constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+    static constexpr int C = ipow(NB, SL);
+    static constexpr int NP = ipow(NB, SL - 1);
+    static constexpr int NZ = NB + 1;
+    static constexpr int S = C * NZ;                   // scores per (t, n)
+    static constexpr int NT = ((C + 31) / 32) * 32;    // threads per CTA
+    static constexpr int W = NT / 32;
+    static constexpr int D0 = 24576 / (S * 4);
+    static constexpr int D = D0 < 2 ? 2 : (D0 > 8 ? 8 : D0);   // ring depth (rows in flight + 1)
+    static_assert(S % 2 == 0, "row must be a whole number of 8-byte chunks");
+};
+
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(float *dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NPEND));
+}
+
+template <int NFLOATS, int NT> __device__ __forceinline__ void copy_row(float *dst, const float *src) {
+    for (int i = threadIdx.x; i < NFLOATS / 2; i += NT) cp_async8(dst + 2 * i, src + 2 * i);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+// xor butterfly: every lane ends with the same bits (a+b == b+a), see oracle/c/crf_exact.c tree_sum()
+__device__ __forceinline__ float warp_sum_tree(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = XB_ADD(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+template <int NZ> __device__ __forceinline__ float lse_exact(const float (&x)[NZ], float m) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NZ; k++) {
+        float e = xb_expf(XB_SUB(x[k], m));
+        s = (k == 0) ? e : XB_ADD(s, e);
+    }
+    return XB_ADD(m, xb_logf(s));
+}
+
+// --------------------------------------------------------------------------------------------------
+// Forward sweep, Log semiring: alpha (T+1,N,C) and / or logZ (N).      grid = N, block = NT
+template <int NB, int SL>
+__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restrict__ alpha_out,
+                 float *__restrict__ logz_out) {
+    using L = Lat<NB, SL>;
+    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
+    extern __shared__ __align__(16) float smem[];
+    float *ring = smem;              // D * S
+    float *a = ring + D * S;         // 2 * NT
+    float *red = a + 2 * NT;         // 2 * W
+    const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
+    const bool act = c < C;
+    const float *base = scores + (size_t)n * S;
+    const size_t row = (size_t)N * S;
+
+#pragma unroll
+    for (int j = 0; j < D - 1; j++) {
+        if (j < T) copy_row<S, NT>(ring + j * S, base + (size_t)j * row);
+        cp_async_commit();
+    }
+    a[c] = 0.0f;
+    if (alpha_out && act) alpha_out[(size_t)n * C + c] = 0.0f;
+    int src[NZ];
+    src[0] = act ? c : 0;
+#pragma unroll
+    for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
+
+    for (int t = 0; t < T; t++) {
+        cp_async_wait<D - 2>();
+        __syncthreads();
+        {
+            int r = t + D - 1;
+            if (r < T) copy_row<S, NT>(ring + (r % D) * S, base + (size_t)r * row);
+            cp_async_commit();
+        }
+        const float *M = ring + (t % D) * S + c * NZ;
+        const float *ac = a + (t & 1) * NT;
+        float *an = a + ((t + 1) & 1) * NT;
+        if (act) {
+            float x[NZ], m;
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                x[k] = XB_ADD(M[k], ac[src[k]]);
+                m = (k == 0) ? x[k] : fmaxf(m, x[k]);
+            }
+            float v = lse_exact<NZ>(x, m);
+            an[c] = v;
+            if (alpha_out) alpha_out[((size_t)(t + 1) * N + n) * C + c] = v;
+        }
+    }
+    __syncthreads();
+    if (logz_out) {
+        float v = act ? a[(T & 1) * NT + c] : -INFINITY;
+        float m = warp_max(v);
+        if (lane == 0) red[w] = m;
+        __syncthreads();
+        m = red[0];
+#pragma unroll
+        for (int i = 1; i < W; i++) m = fmaxf(m, red[i]);
+        float e = act ? xb_expf(XB_SUB(v, m)) : 0.0f;
+        e = warp_sum_tree(e);
+        if (lane == 0) red[W + w] = e;
+        __syncthreads();
+        if (c == 0) {
+            float s = red[W];
+            for (int i = 1; i < W; i++) s = XB_ADD(s, red[W + i]);
+            logz_out[n] = XB_ADD(m, xb_logf(s));
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Plain backward scan over the raw scores in either semiring: out (T+1,N,C).  Used for
+// CTC_CRF.backward_scores (Log) and for the Max-beta of CTC_CRF.viterbi on arbitrary scores.
+template <int NB, int SL, bool USE_MAX>
+__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+crf_bscan_kernel(const float *__restrict__ scores, int T, int N, float *__restrict__ out) {
+    using L = Lat<NB, SL>;
+    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, D = L::D;
+    extern __shared__ __align__(16) float smem[];
+    float *ring = smem;
+    float *b = ring + D * S;         // 2 * NT
+    const int n = blockIdx.x, c = threadIdx.x;
+    const bool act = c < C;
+    const float *base = scores + (size_t)n * S;
+    const size_t row = (size_t)N * S;
+#pragma unroll
+    for (int j = 0; j < D - 1; j++) {
+        if (j < T) copy_row<S, NT>(ring + j * S, base + (size_t)(T - 1 - j) * row);
+        cp_async_commit();
+    }
+    b[c] = 0.0f;
+    if (act) out[((size_t)T * N + n) * C + c] = 0.0f;
+    const int kk = act ? 1 + c / L::NP : 1, cb = act ? (c % L::NP) * NB : 0;
+    for (int i = 0; i < T; i++) {
+        const int t = T - 1 - i;
+        cp_async_wait<D - 2>();
+        __syncthreads();
+        {
+            int r = i + D - 1;
+            if (r < T) copy_row<S, NT>(ring + (r % D) * S, base + (size_t)(T - 1 - r) * row);
+            cp_async_commit();
+        }
+        const float *M = ring + (i % D) * S;
+        const float *b1 = b + (i & 1) * NT;
+        float *b0 = b + ((i + 1) & 1) * NT;
+        if (act) {
+            float y[NZ], m;
+            y[0] = XB_ADD(M[c * NZ], b1[c]);
+            m = y[0];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                y[1 + j] = XB_ADD(M[(cb + j) * NZ + kk], b1[cb + j]);
+                m = fmaxf(m, y[1 + j]);
+            }
+            float v = USE_MAX ? m : lse_exact<NZ>(y, m);
+            b0[c] = v;
+            out[((size_t)t * N + n) * C + c] = v;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Fused backward sweep of decode_batch: per step t (descending)
+//   x = (M + alpha_t[idx]) + beta_{t+1};  p = softmax_{C*NZ}(x);  lp = log(p + 1e-8)
+//   beta_t (Log) from M and beta_{t+1};   bmax_t (Max semiring over lp) from lp and bmax_{t+1}
+// writes lp (T,N,S) and bmax (T+1,N,C) for the Max forward sweep, optionally post (T,N,S).
+template <int NB, int SL>
+__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ alpha, int T, int N,
+                    float *__restrict__ lp_out, float *__restrict__ bmax_out, float *__restrict__ post_out) {
+    using L = Lat<NB, SL>;
+    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
+    extern __shared__ __align__(16) float smem[];
+    float *ringM = smem;                 // D * S
+    float *LP = ringM + D * S;           // S
+    float *ringA = LP + S;               // D * NT
+    float *beta = ringA + D * NT;        // 2 * NT
+    float *bm = beta + 2 * NT;           // 2 * NT
+    float *red = bm + 2 * NT;            // 2 * W
+    const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
+    const bool act = c < C;
+    const float *base = scores + (size_t)n * S;
+    const size_t row = (size_t)N * S;
+    const float *abase = alpha + (size_t)n * C;
+    const size_t arow = (size_t)N * C;
+
+#pragma unroll
+    for (int j = 0; j < D - 1; j++) {
+        if (j < T) {
+            copy_row<S, NT>(ringM + j * S, base + (size_t)(T - 1 - j) * row);
+            if (act) cp_async4(ringA + j * NT + c, abase + (size_t)(T - 1 - j) * arow + c);
+        }
+        cp_async_commit();
+    }
+    beta[c] = 0.0f;
+    bm[c] = 0.0f;
+    if (act) bmax_out[((size_t)T * N + n) * C + c] = 0.0f;
+    int src[NZ];
+    src[0] = act ? c : 0;
+#pragma unroll
+    for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
+    const int kk = act ? 1 + c / L::NP : 1, cb = act ? (c % L::NP) * NB : 0;
+
+    for (int i = 0; i < T; i++) {
+        const int t = T - 1 - i;
+        cp_async_wait<D - 2>();
+        __syncthreads();                                                        // B0
+        {
+            int r = i + D - 1;
+            if (r < T) {
+                copy_row<S, NT>(ringM + (r % D) * S, base + (size_t)(T - 1 - r) * row);
+                if (act) cp_async4(ringA + (r % D) * NT + c, abase + (size_t)(T - 1 - r) * arow + c);
+            }
+            cp_async_commit();
+        }
+        const float *M = ringM + (i % D) * S;
+        const float *A = ringA + (i % D) * NT;
+        const float *b1 = beta + (i & 1) * NT;
+        float *b0 = beta + ((i + 1) & 1) * NT;
+        const float *m1 = bm + (i & 1) * NT;
+        float *m0 = bm + ((i + 1) & 1) * NT;
+
+        float x[NZ], lmax = -INFINITY;
+        if (act) {
+            const float bc = b1[c];
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                x[k] = XB_ADD(XB_ADD(M[c * NZ + k], A[src[k]]), bc);
+                lmax = fmaxf(lmax, x[k]);
+            }
+            // Log beta_t[c]: edges leaving c = stay, then the n_base moves
+            float y[NZ], m;
+            y[0] = XB_ADD(M[c * NZ], bc);
+            m = y[0];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                y[1 + j] = XB_ADD(M[(cb + j) * NZ + kk], b1[cb + j]);
+                m = fmaxf(m, y[1 + j]);
+            }
+            b0[c] = lse_exact<NZ>(y, m);
+        }
+        float wm = warp_max(lmax);
+        if (lane == 0) red[w] = wm;
+        __syncthreads();                                                        // B1
+        float gmax = red[0];
+#pragma unroll
+        for (int j = 1; j < W; j++) gmax = fmaxf(gmax, red[j]);
+        float s = 0.0f;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                x[k] = xb_expf(XB_SUB(x[k], gmax));
+                s = (k == 0) ? x[k] : XB_ADD(s, x[k]);
+            }
+        }
+        s = warp_sum_tree(s);
+        if (lane == 0) red[W + w] = s;
+        __syncthreads();                                                        // B2
+        float tot = red[W];
+#pragma unroll
+        for (int j = 1; j < W; j++) tot = XB_ADD(tot, red[W + j]);
+        const float inv = XB_RCP(tot);
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                float p = XB_MUL(x[k], inv);
+                if (post_out) post_out[((size_t)t * N + n) * S + c * NZ + k] = p;
+                LP[c * NZ + k] = xb_logf(XB_ADD(p, XB_POST_EPS));
+            }
+        }
+        __syncthreads();                                                        // B3
+        {
+            float2 *dst = reinterpret_cast<float2 *>(lp_out + ((size_t)t * N + n) * S);
+            const float2 *srcv = reinterpret_cast<const float2 *>(LP);
+            for (int j = c; j < S / 2; j += NT) dst[j] = srcv[j];
+        }
+        if (act) {
+            float m = XB_ADD(LP[c * NZ], m1[c]);
+#pragma unroll
+            for (int j = 0; j < NB; j++) m = fmaxf(m, XB_ADD(LP[(cb + j) * NZ + kk], m1[cb + j]));
+            m0[c] = m;
+            bmax_out[((size_t)t * N + n) * C + c] = m;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Forward sweep, Max semiring, over lp with the stored Max-beta: arg-max edge per step -> label
+// (edge % NZ), then path_to_str + left-pack for the row.   dynamic smem tail holds T labels.
+struct Alphabet { char ch[16]; };
+
+template <int NB, int SL>
+__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ bmax, int T, int N,
+                       int8_t *__restrict__ labels_out, int8_t *__restrict__ seq_out,
+                       int8_t *__restrict__ qs_out, int32_t *__restrict__ lens_out, Alphabet abc) {
+    using L = Lat<NB, SL>;
+    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
+    extern __shared__ __align__(16) float smem[];
+    float *ring = smem;                  // D * S
+    float *ringB = ring + D * S;         // D * NT
+    float *am = ringB + D * NT;          // 2 * NT
+    float *bval = am + 2 * NT;           // 2 * W
+    int *bidx = reinterpret_cast<int *>(bval + 2 * W);      // 2 * W
+    int *scan = bidx + 2 * W;            // NT + 1
+    int8_t *lab = reinterpret_cast<int8_t *>(scan + NT + 1);   // T
+    const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
+    const bool act = c < C;
+    const float *base = lp + (size_t)n * S;
+    const size_t row = (size_t)N * S;
+    const float *bbase = bmax + (size_t)n * C;
+    const size_t brow = (size_t)N * C;
+
+#pragma unroll
+    for (int j = 0; j < D - 1; j++) {
+        if (j < T) {
+            copy_row<S, NT>(ring + j * S, base + (size_t)j * row);
+            if (act) cp_async4(ringB + j * NT + c, bbase + (size_t)(j + 1) * brow + c);
+        }
+        cp_async_commit();
+    }
+    am[c] = 0.0f;
+    int src[NZ];
+    src[0] = act ? c : 0;
+#pragma unroll
+    for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
+
+    for (int t = 0; t < T; t++) {
+        cp_async_wait<D - 2>();
+        __syncthreads();
+        {
+            int r = t + D - 1;
+            if (r < T) {
+                copy_row<S, NT>(ring + (r % D) * S, base + (size_t)r * row);
+                if (act) cp_async4(ringB + (r % D) * NT + c, bbase + (size_t)(r + 1) * brow + c);
+            }
+            cp_async_commit();
+        }
+        if (c == 0 && t > 0) {           // finish step t-1: reduce the per-warp candidates
+            const int q = (t - 1) & 1;
+            float bv = bval[q * W];
+            int bi = bidx[q * W];
+            for (int j = 1; j < W; j++) {
+                float v = bval[q * W + j];
+                int ix = bidx[q * W + j];
+                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+            }
+            lab[t - 1] = (int8_t)(bi % NZ);
+        }
+        const float *M = ring + (t % D) * S + c * NZ;
+        const float *ac = am + (t & 1) * NT;
+        float *an = am + ((t + 1) & 1) * NT;
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        if (act) {
+            const float bc = ringB[(t % D) * NT + c];
+            float m;
+#pragma unroll
+            for (int k = 0; k < NZ; k++) {
+                float v = XB_ADD(M[k], ac[src[k]]);
+                m = (k == 0) ? v : fmaxf(m, v);
+                float sc = XB_ADD(v, bc);
+                if (k == 0 || sc > best) { best = sc; besti = c * NZ + k; }
+            }
+            an[c] = m;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { bval[(t & 1) * W + w] = best; bidx[(t & 1) * W + w] = besti; }
+    }
+    __syncthreads();
+    if (c == 0 && T > 0) {
+        const int q = (T - 1) & 1;
+        float bv = bval[q * W];
+        int bi = bidx[q * W];
+        for (int j = 1; j < W; j++) {
+            float v = bval[q * W + j];
+            int ix = bidx[q * W + j];
+            if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        }
+        lab[T - 1] = (int8_t)(bi % NZ);
+    }
+    __syncthreads();
+
+    // labels (N,T) and left-packed letters: thread c owns steps [c*per, (c+1)*per)
+    if (labels_out)
+        for (int t = c; t < T; t += NT) labels_out[(size_t)n * T + t] = lab[t];
+    if (seq_out) {
+        const int per = (T + NT - 1) / NT;
+        const int lo = min(c * per, T), hi = min(lo + per, T);
+        int cnt = 0;
+        for (int t = lo; t < hi; t++) cnt += lab[t] != 0;
+        scan[c + 1] = cnt;
+        if (c == 0) scan[0] = 0;
+        __syncthreads();
+        if (c == 0)
+            for (int j = 1; j <= NT; j++) scan[j] += scan[j - 1];
+        __syncthreads();
+        int pos = scan[c];
+        const int total = scan[NT];
+        for (int t = lo; t < hi; t++) {
+            int l = lab[t];
+            if (l != 0) {
+                seq_out[(size_t)n * T + pos] = (int8_t)abc.ch[l];
+                if (qs_out) qs_out[(size_t)n * T + pos] = (int8_t)'O';
+                pos++;
+            }
+        }
+        for (int p = total + c; p < T; p += NT) {
+            seq_out[(size_t)n * T + p] = 0;
+            if (qs_out) qs_out[(size_t)n * T + p] = 0;
+        }
+        if (c == 0 && lens_out) lens_out[n] = total;
+    }
+}
+
+template <int NB, int SL> size_t smem_alpha() {
+    using L = Lat<NB, SL>;
+    return sizeof(float) * (L::D * L::S + 2 * L::NT + 2 * L::W);
+}
+template <int NB, int SL> size_t smem_bscan() {
+    using L = Lat<NB, SL>;
+    return sizeof(float) * (L::D * L::S + 2 * L::NT);
+}
+template <int NB, int SL> size_t smem_backward() {
+    using L = Lat<NB, SL>;
+    return sizeof(float) * (L::D * L::S + L::S + L::D * L::NT + 4 * L::NT + 2 * L::W);
+}
+template <int NB, int SL> size_t smem_vit(int T) {
+    using L = Lat<NB, SL>;
+    return sizeof(float) * (L::D * L::S + L::D * L::NT + 2 * L::NT + 4 * L::W + L::NT + 1) + ((T + 15) / 16) * 16;
+}
+
+template <typename K> int set_smem(xb_handle *h, K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) XB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return XB_OK;
+}
+
+template <int NB, int SL>
+int alpha_impl(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s) {
+    using L = Lat<NB, SL>;
+    auto k = crf_alpha_kernel<NB, SL>;
+    size_t sm = smem_alpha<NB, SL>();
+    if (int rc = set_smem(h, k, sm)) return rc;
+    k<<<N, L::NT, sm, s>>>(scores, T, N, alpha, logz);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+template <int NB, int SL>
+int backward_impl(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
+                  float *post, float *beta, int mode, cudaStream_t s) {
+    using L = Lat<NB, SL>;
+    if (mode == 0) {
+        auto k = crf_backward_kernel<NB, SL>;
+        size_t sm = smem_backward<NB, SL>();
+        if (int rc = set_smem(h, k, sm)) return rc;
+        k<<<N, L::NT, sm, s>>>(scores, alpha, T, N, lp, bmax, post);
+    } else if (mode == 1) {
+        auto k = crf_bscan_kernel<NB, SL, true>;
+        size_t sm = smem_bscan<NB, SL>();
+        if (int rc = set_smem(h, k, sm)) return rc;
+        k<<<N, L::NT, sm, s>>>(scores, T, N, bmax);
+    } else {
+        auto k = crf_bscan_kernel<NB, SL, false>;
+        size_t sm = smem_bscan<NB, SL>();
+        if (int rc = set_smem(h, k, sm)) return rc;
+        k<<<N, L::NT, sm, s>>>(scores, T, N, beta);
+    }
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+template <int NB, int SL>
+int vit_impl(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels, int8_t *seq,
+             int8_t *qs, int32_t *lens, cudaStream_t s) {
+    using L = Lat<NB, SL>;
+    auto k = crf_viterbi_fwd_kernel<NB, SL>;
+    size_t sm = smem_vit<NB, SL>(T);
+    if (int rc = set_smem(h, k, sm)) return rc;
+    Alphabet abc;
+    for (int i = 0; i < 16; i++) abc.ch[i] = h->alphabet[i];
+    k<<<N, L::NT, sm, s>>>(lp, bmax, T, N, labels, seq, qs, lens, abc);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+#define XB_LATTICE_DISPATCH(h, CALL)                                                               \
+    switch ((h)->n_base * 10 + (h)->state_len) {                                                   \
+        case 43: return CALL(4, 3);                                                                \
+        case 53: return CALL(5, 3);                                                                \
+        case 63: return CALL(6, 3);                                                                \
+        case 44: return CALL(4, 4);                                                                \
+        case 22: return CALL(2, 2);                                                                \
+        default:                                                                                   \
+            return xb_fail((h), XB_ERR_UNSUPPORTED, "no CRF kernel compiled for n_base=%d state_len=%d", \
+                           (h)->n_base, (h)->state_len);                                           \
+    }
+
+}  // namespace
+
+int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s) {
+#define CALL(NB, SL) alpha_impl<NB, SL>(h, scores, T, N, alpha, logz, s)
+    XB_LATTICE_DISPATCH(h, CALL)
+#undef CALL
+}
+
+// mode 0: fused decode backward sweep (needs alpha; writes lp, bmax, optional post)
+// mode 1: Max-semiring backward scan of the raw scores into bmax;  mode 2: Log-semiring scan into beta
+int xb_decode_backward(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
+                       float *post, float *beta, int mode, cudaStream_t s) {
+#define CALL(NB, SL) backward_impl<NB, SL>(h, scores, alpha, T, N, lp, bmax, post, beta, mode, s)
+    XB_LATTICE_DISPATCH(h, CALL)
+#undef CALL
+}
+
+int xb_decode_viterbi_fwd(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels,
+                          int8_t *seq, int8_t *qstring, int32_t *lens, cudaStream_t s) {
+#define CALL(NB, SL) vit_impl<NB, SL>(h, lp, bmax, T, N, labels, seq, qstring, lens, s)
+    XB_LATTICE_DISPATCH(h, CALL)
+#undef CALL
+}

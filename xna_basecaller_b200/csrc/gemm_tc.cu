@@ -1,0 +1,295 @@
+// tcgen05 + TMA GEMM for sm_100a with fused epilogues:  D(M,N) = A(M,K) . B(N,K)^T, 16-bit K-major operands,
+// fp32 accumulation in tensor memory.  One 128x128 output tile per CTA, 64-wide K blocks through a TMA ->
+// mbarrier -> tcgen05.mma ring, two CTAs per SM so that one CTA's epilogue overlaps the other's main loop.
+//
+// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (warp q reads TMEM lanes 32q..32q+31 = tile rows).
+//
+// Epilogues
+//   EPI_F32    plain fp32 store (self test)
+//   EPI_CONV3  third Convolution of the stem as an implicit GEMM over im2col rows: + bias, swish, 16-bit store
+//              in (T, N, 768) order, which absorbs nn.Permute([2,0,1])       (bonito/nn.py:57-68,156-167)
+//   EPI_INPROJ LSTM input projection x_t W_ih^T + (b_ih + b_hh) for all t at once, 16-bit store (nn.py:189-193)
+//   EPI_HEAD   LinearCRFEncoder: scale * tanh(x W^T + b), blank score inserted in front of every group of
+//              n_base columns -> fp32 (T, N, C*NZ)                            (bonito/nn.py:112-133)
+//   EPI_LSTM   one LSTM time step: gates = acc (h_{t-1} W_hh^T) + G[t]; c, h update in fp32; h stored 16-bit.
+//              Columns of a tile are [i | f | g | o] x 32 hidden units (weights are row-permuted at load time).
+#include "xb_common.cuh"
+#include "xb_ptx.cuh"
+#include "xb_gemm.cuh"
+
+using namespace xbptx;
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 3;
+constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+template <bool BF16, int EPI>
+__global__ void __launch_bounds__(256, EPI == EPI_LSTM ? 1 : 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int kblocks = (EPI == EPI_LSTM && p.first) ? 0 : p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < kblocks; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                uint8_t *sa = smem + s * STAGE_BYTES;
+                tma_load_2d(sa, &tmA, &full[s], kb * BK, m0 + p.a_row_offset);
+                tma_load_2d(sa + TILE_A_BYTES, &tmB, &full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, BM, BN);
+        for (int kb = 0; kb < kblocks; kb++) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + TILE_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    mma_f16_ss(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                               (kb | k) != 0);
+                }
+                mma_commit(&empty[s]);
+                if (kb == kblocks - 1) mma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;             // tile row == TMEM lane
+        const int m = m0 + r;
+        const bool row_ok = m < p.M;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (kblocks > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        using X = xb16<BF16>;
+        if constexpr (EPI == EPI_LSTM) {
+            // row = batch element; columns [g*32 + u], g in (i,f,g,o), u = unit within the 32-unit slice
+            const int unit0 = blockIdx.x * 32;
+            const size_t grow = ((size_t)p.t_cur * p.NB + m) * XB_GATES + n0;
+            const uint16_t *G = reinterpret_cast<const uint16_t *>(p.gates) + grow;
+            float *cst = p.cstate + (size_t)m * XB_FEATURES + unit0;
+            uint16_t *hout = reinterpret_cast<uint16_t *>(p.out) + ((size_t)p.t_cur * p.NB + m) * XB_FEATURES + unit0;
+#pragma unroll 1
+            for (int ub = 0; ub < 32; ub += 8) {
+                uint32_t acc[4][8];
+                if (kblocks > 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) tmem_ld_32x32b_x8(taddr + g * 32 + ub, acc[g]);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) acc[g][j] = 0u;
+                }
+                if (row_ok) {
+                    float gv[4][8];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        uint4 raw = *reinterpret_cast<const uint4 *>(G + g * 32 + ub);
+                        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            float2 f = X::unpack(rw[j]);
+                            gv[g][2 * j] = __uint_as_float(acc[g][2 * j]) + f.x;
+                            gv[g][2 * j + 1] = __uint_as_float(acc[g][2 * j + 1]) + f.y;
+                        }
+                    }
+                    float cprev[8];
+                    if (p.first) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) cprev[j] = 0.0f;
+                    } else {
+                        float4 c0 = *reinterpret_cast<const float4 *>(cst + ub);
+                        float4 c1 = *reinterpret_cast<const float4 *>(cst + ub + 4);
+                        cprev[0] = c0.x; cprev[1] = c0.y; cprev[2] = c0.z; cprev[3] = c0.w;
+                        cprev[4] = c1.x; cprev[5] = c1.y; cprev[6] = c1.z; cprev[7] = c1.w;
+                    }
+                    float cn[8], hn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float ig = fast_sigmoid(gv[0][j]), fg = fast_sigmoid(gv[1][j]);
+                        float gg = fast_tanh(gv[2][j]), og = fast_sigmoid(gv[3][j]);
+                        cn[j] = fg * cprev[j] + ig * gg;
+                        hn[j] = og * fast_tanh(cn[j]);
+                    }
+                    *reinterpret_cast<float4 *>(cst + ub) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    *reinterpret_cast<float4 *>(cst + ub + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    uint4 hv;
+                    hv.x = X::pack(hn[0], hn[1]); hv.y = X::pack(hn[2], hn[3]);
+                    hv.z = X::pack(hn[4], hn[5]); hv.w = X::pack(hn[6], hn[7]);
+                    *reinterpret_cast<uint4 *>(hout + ub) = hv;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(taddr + cb, acc);
+                tmem_ld_wait();
+                const int nb = n0 + cb;
+                if (!row_ok) {
+                    // nothing to store for rows past M (the TMEM load above is warp-collective)
+                } else if constexpr (EPI == EPI_F32) {
+                    float *o = reinterpret_cast<float *>(p.out) + (size_t)m * p.ldo + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (nb + j < p.N) o[j] = __uint_as_float(acc[j]);
+                } else if constexpr (EPI == EPI_CONV3 || EPI == EPI_INPROJ) {
+                    size_t orow;
+                    if constexpr (EPI == EPI_CONV3) {
+                        const int b = m / p.T, t = m - b * p.T;       // im2col rows are (chunk, t)
+                        orow = (size_t)t * p.NB + b;
+                    } else {
+                        orow = (size_t)m;
+                    }
+                    uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldo + nb;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float v0 = __uint_as_float(acc[2 * j]) + __ldg(p.bias + nb + 2 * j);
+                        float v1 = __uint_as_float(acc[2 * j + 1]) + __ldg(p.bias + nb + 2 * j + 1);
+                        if constexpr (EPI == EPI_CONV3) {
+                            v0 = v0 * fast_sigmoid(v0);
+                            v1 = v1 * fast_sigmoid(v1);
+                        }
+                        pk[j] = X::pack(v0, v1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        reinterpret_cast<uint4 *>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                } else if constexpr (EPI == EPI_HEAD) {
+                    float *o = reinterpret_cast<float *>(p.out) + (size_t)m * p.ldo;
+#pragma unroll 4
+                    for (int j = 0; j < 32; j++) {
+                        const int col = nb + j;
+                        if (col < p.head_rows) {
+                            float v = p.scale * fast_tanh(__uint_as_float(acc[j]) + __ldg(p.bias + col));
+                            if (p.expand) {
+                                const int c = col / p.n_base, e = col - c * p.n_base;
+                                float *dst = o + c * (p.n_base + 1);
+                                if (e == 0) dst[0] = p.blank;
+                                dst[1 + e] = v;
+                            } else {
+                                o[col] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+// 2-D K-major tensor map: rows x K 16-bit elements, row pitch ld elements, box 64 x 128, 128B swizzle.
+int xb_make_tmap_2d(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint64_t ld) {
+    if (!h->encode_tiled) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return xb_fail(h, XB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        h->encode_tiled = fn;
+    }
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
+        out, h->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims,
+        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return xb_fail(h, XB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return XB_OK;
+}
+
+template <bool BF16, int EPI>
+static int launch_one(xb_handle *h, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int rows_a,
+                      cudaStream_t s) {
+    auto k = gemm_tc_kernel<BF16, EPI>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        XB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (rows_a + BM - 1) / BM);
+    k<<<grid, 256, SMEM_BYTES, s>>>(tmA, tmB, p);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p,
+                   cudaStream_t s) {
+    if (p.K % BK != 0) return xb_fail(h, XB_ERR_ARG, "GEMM K=%d is not a multiple of %d", p.K, BK);
+#define XB_EPI_CASE(E)                                                                       \
+    case E:                                                                                  \
+        return h->bf16 ? launch_one<true, E>(h, tmA, tmB, p, p.M, s) : launch_one<false, E>(h, tmA, tmB, p, p.M, s);
+    switch (epi) {
+        XB_EPI_CASE(EPI_F32)
+        XB_EPI_CASE(EPI_CONV3)
+        XB_EPI_CASE(EPI_INPROJ)
+        XB_EPI_CASE(EPI_HEAD)
+        XB_EPI_CASE(EPI_LSTM)
+    }
+#undef XB_EPI_CASE
+    return xb_fail(h, XB_ERR_ARG, "unknown epilogue %d", epi);
+}

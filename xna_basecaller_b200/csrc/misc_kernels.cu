@@ -1,0 +1,135 @@
+// Overlap stitching of left-packed chunk rows and the CTC-CRF training loss forward.
+//
+//   stitch:   bonito/util.py:169-188 (stitch) applied by bonito/crf/basecall.py:15-24 (stitch_results) to the
+//             left-packed (n_chunks, T) int8 rows of compute_scores, followed by koi.decode.to_str
+//             (crf/basecall.py:85-93): zeros dropped.  Slices act on ROW POSITIONS of the packed rows -- the
+//             reference's behaviour, kept on purpose.
+//   ctc loss: CTC_CRF.ctc_loss / normalise / prepare_ctc_scores (bonito/crf/model.py:48-49,102-131) with
+//             seqdist.ctc_simple.logZ_cupy restated as a stay/move lattice scan.
+#include "xb_common.cuh"
+#include "xb_exact_math.h"
+
+namespace {
+
+// one warp per read
+__global__ void stitch_kernel(const int8_t *__restrict__ rows, int T, const int32_t *__restrict__ chunk_first,
+                              const int32_t *__restrict__ chunk_count, const int32_t *__restrict__ read_len, int n_reads,
+                              int chunksize, int overlap, int stride, int8_t *__restrict__ out, int out_stride,
+                              int32_t *__restrict__ out_len) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const int nch = chunk_count[r], first = chunk_first[r], length = read_len[r];
+    const int semi = overlap / 2;
+    const int start = semi / stride, end = (chunksize - semi) / stride;
+    const int stub = (length - overlap) % (chunksize - overlap);
+    const int first_end = stub > 0 ? (stub + semi) / stride : end;
+    int8_t *o = out + (size_t)r * out_stride;
+    int pos = 0;
+    for (int ci = 0; ci < nch; ci++) {
+        int lo, hi;
+        if (nch == 1) { lo = 0; hi = T; }
+        else if (ci == 0) { lo = 0; hi = first_end; }
+        else if (ci == nch - 1) { lo = start; hi = T; }
+        else { lo = start; hi = end; }
+        lo = max(0, min(lo, T));
+        hi = max(lo, min(hi, T));
+        const int8_t *row = rows + (size_t)(first + ci) * T;
+        for (int base = lo; base < hi; base += 32) {
+            int i = base + lane;
+            int8_t v = (i < hi) ? row[i] : (int8_t)0;
+            unsigned mask = __ballot_sync(0xffffffffu, v != 0);
+            if (v != 0) {
+                int p = pos + __popc(mask & ((1u << lane) - 1));
+                if (p < out_stride) o[p] = v;
+            }
+            pos += __popc(mask);
+        }
+    }
+    if (lane == 0) out_len[r] = min(pos, out_stride);
+}
+
+// ---- CTC-CRF loss -----------------------------------------------------------------------------------
+__device__ __forceinline__ float logaddexp_exact(float a, float b) {
+    float m = fmaxf(a, b);
+    float s = XB_ADD(xb_expf(XB_SUB(a, m)), xb_expf(XB_SUB(b, m)));
+    return XB_ADD(m, xb_logf(s));
+}
+
+// grid = N, block = NT (multiple of 32, >= n positions).  dynamic smem: 2*NT floats + row ring
+__global__ void ctc_simple_kernel(const float *__restrict__ scores, int T, int N, int S, const int32_t *__restrict__ targets,
+                                  int Lmax, const int32_t *__restrict__ lengths, const float *__restrict__ logz,
+                                  int normalise, int n_base, int state_len, float *__restrict__ loss) {
+    extern __shared__ __align__(16) float sm[];
+    const int NT = blockDim.x, j = threadIdx.x, n = blockIdx.x;
+    float *a = sm;                   // 2 * NT
+    float *rowbuf = sm + 2 * NT;     // 2 * S  (double buffered score row)
+    const int npos = Lmax - (state_len - 1);
+    const int NZ = n_base + 1;
+    const int32_t *tg = targets + (size_t)n * Lmax;
+    const bool act = j < npos;
+    // stay edge of position j, and the move edge ENTERING position j (move_indices[j-1] of
+    // crf/model.py:113 = stay_indices[j] + targets[j-1] + 1)
+    int stay_idx = 0, move_in = 0;
+    if (act) {
+        int st = 0;
+        for (int i = 0; i < state_len; i++) st = st * n_base + max(tg[j + i] - 1, 0);
+        stay_idx = st * NZ;
+        if (j > 0) move_in = stay_idx + max(tg[j - 1] - 1, 0) + 1;
+    }
+    const float shift = normalise ? logz[n] / (float)T : 0.0f;
+    a[j] = (j == 0) ? 0.0f : XB_NEG_BIG;
+    const float *base = scores + (size_t)n * S;
+    const size_t row = (size_t)N * S;
+    for (int i = j; i < S; i += NT) rowbuf[i] = base[i];
+    __syncthreads();
+    for (int t = 0; t < T; t++) {
+        const float *M = rowbuf + (t & 1) * S;
+        float *Mn = rowbuf + ((t + 1) & 1) * S;
+        if (t + 1 < T)
+            for (int i = j; i < S; i += NT) Mn[i] = base[(size_t)(t + 1) * row + i];
+        const float *ac = a + (t & 1) * NT;
+        float *an = a + ((t + 1) & 1) * NT;
+        if (act) {
+            float v = XB_ADD(XB_SUB(M[stay_idx], shift), ac[j]);
+            if (j > 0) v = logaddexp_exact(v, XB_ADD(XB_SUB(M[move_in], shift), ac[j - 1]));
+            an[j] = v;
+        } else {
+            an[j] = XB_NEG_BIG;
+        }
+        __syncthreads();
+    }
+    if (j == 0) {
+        const int len = lengths[n];
+        const int last = len + 1 - state_len - 1;
+        float z = (last >= 0 && last < npos) ? a[(T & 1) * NT + last] : XB_NEG_BIG;
+        loss[n] = -z / (float)len;
+    }
+}
+
+}  // namespace
+
+int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
+                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out,
+                   int out_stride, int32_t *out_len, cudaStream_t s) {
+    XB_REQUIRE(h, n_reads > 0 && chunksize > overlap && stride > 0, "bad stitch arguments");
+    const int warps = 4;
+    stitch_kernel<<<(n_reads + warps - 1) / warps, warps * 32, 0, s>>>(rows, T, chunk_first, chunk_count, read_len, n_reads,
+                                                                       chunksize, overlap, stride, out, out_stride, out_len);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                     const int32_t *lengths, int normalise, float *loss, cudaStream_t s) {
+    const int npos = Lmax - (h->state_len - 1);
+    XB_REQUIRE(h, npos >= 1 && npos <= 1024, "Lmax=%d unsupported (1 <= Lmax-state_len+1 <= 1024)", Lmax);
+    if (normalise)
+        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, s)) return rc;
+    const int NT = ((npos + 31) / 32) * 32;
+    const int S = h->C * h->NZ;
+    size_t smem = sizeof(float) * (2 * NT + 2 * S);
+    ctc_simple_kernel<<<N, NT, smem, s>>>(scores, T, N, S, targets, Lmax, lengths, h->logz, normalise, h->n_base,
+                                         h->state_len, loss);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}

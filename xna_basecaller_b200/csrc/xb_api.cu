@@ -1,0 +1,421 @@
+// C ABI of libxna_b200.so (include/xna_basecaller.h): handle life cycle, weight repacking, the encoder
+// pipeline (conv stem -> 5 LSTM layers -> CRF head), the CRF decode entry points and the host-buffer call.
+#include <stdarg.h>
+#include <string.h>
+
+#include "xb_common.cuh"
+#include "xb_gemm.cuh"
+
+thread_local std::string xb_global_err;
+
+int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    xb_global_err = buf;
+    return code;
+}
+
+int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
+int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                     const int32_t *lengths, int normalise, float *loss, cudaStream_t s);
+int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
+                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out,
+                   int out_stride, int32_t *out_len, cudaStream_t s);
+
+namespace {
+
+int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
+
+template <typename T> int dev_alloc(xb_handle *h, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess)
+        return xb_fail(h, XB_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    *p = reinterpret_cast<T *>(q);
+    return XB_OK;
+}
+int dev_alloc_bytes(xb_handle *h, void **p, size_t bytes) { return dev_alloc<uint8_t>(h, reinterpret_cast<uint8_t **>(p), bytes); }
+
+// ---- weight repacking ------------------------------------------------------------------------------
+// dst (rows_dst, cols_dst) 16-bit <- src fp32; mode 0: plain rows (zero padding past rows_src / cols_src);
+// mode 1: LSTM gate interleave, dst row j*128 + g*32 + u <- src row g*768 + j*32 + u;
+// mode 2: conv3 (768,16,19) -> (768, 320) with column tap*16 + ch.
+template <bool BF16>
+__global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restrict__ dst, int rows_dst, int cols_dst,
+                              int rows_src, int cols_src, int mode) {
+    using X = xb16<BF16>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows_dst * cols_dst) return;
+    int r = (int)(i / cols_dst), c = (int)(i % cols_dst);
+    float v = 0.0f;
+    if (mode == 0) {
+        if (r < rows_src && c < cols_src) v = src[(size_t)r * cols_src + c];
+    } else if (mode == 1) {
+        int j = r >> 7, g = (r >> 5) & 3, u = r & 31;
+        v = src[(size_t)(g * XB_FEATURES + j * 32 + u) * cols_src + c];
+    } else {
+        int tap = c >> 4, ch = c & 15;
+        if (tap < XB_WINLEN) v = src[((size_t)r * XB_C2_CH + ch) * XB_WINLEN + tap];
+    }
+    typename X::T hv = X::from(v);
+    dst[i] = *reinterpret_cast<uint16_t *>(&hv);
+}
+__global__ void lstm_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ dst) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= XB_GATES) return;
+    int j = r >> 7, g = (r >> 5) & 3, u = r & 31;
+    int s = g * XB_FEATURES + j * 32 + u;
+    dst[r] = b_ih[s] + b_hh[s];
+}
+
+int repack(xb_handle *h, const float *src, void *dst, int rows_dst, int cols_dst, int rows_src, int cols_src, int mode,
+           cudaStream_t s) {
+    size_t n = (size_t)rows_dst * cols_dst;
+    int blocks = (int)((n + 255) / 256);
+    if (h->bf16)
+        repack_kernel<true><<<blocks, 256, 0, s>>>(src, reinterpret_cast<uint16_t *>(dst), rows_dst, cols_dst, rows_src, cols_src, mode);
+    else
+        repack_kernel<false><<<blocks, 256, 0, s>>>(src, reinterpret_cast<uint16_t *>(dst), rows_dst, cols_dst, rows_src, cols_src, mode);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+int check_tn(xb_handle *h, int T, int N) {
+    XB_REQUIRE(h, T > 0 && N > 0, "T and N must be positive (got T=%d N=%d)", T, N);
+    XB_REQUIRE(h, T <= h->max_T && N <= h->max_N, "T=%d N=%d exceed the handle capacity max_T=%d max_N=%d", T, N, h->max_T,
+               h->max_N);
+    return XB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xb_abi_version(void) { return XB_ABI_VERSION; }
+
+const char *xb_last_error(const xb_handle *h) { return h ? h->err.c_str() : xb_global_err.c_str(); }
+
+int64_t xb_launch_count(const xb_handle *h) { return h ? h->launches : 0; }
+
+int xb_create(xb_handle **out, int device, int max_N, int max_T, int n_base, int state_len, const char *alphabet, int flags) {
+    if (!out) return xb_fail(nullptr, XB_ERR_ARG, "xb_create: out is NULL");
+    *out = nullptr;
+    if (max_N <= 0 || max_T <= 0) return xb_fail(nullptr, XB_ERR_ARG, "xb_create: max_N and max_T must be positive");
+    if (!alphabet || (int)strlen(alphabet) != n_base + 1 || n_base + 1 > 15)
+        return xb_fail(nullptr, XB_ERR_ARG, "xb_create: alphabet must have n_base+1 letters (blank first)");
+    int key = n_base * 10 + state_len;
+    if (!(key == 43 || key == 53 || key == 63 || key == 44 || key == 22))
+        return xb_fail(nullptr, XB_ERR_UNSUPPORTED, "xb_create: no kernels for n_base=%d state_len=%d", n_base, state_len);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return xb_fail(nullptr, XB_ERR_CUDA, "xb_create: no CUDA device (%s); this library has no CPU path",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return xb_fail(nullptr, XB_ERR_ARG, "xb_create: device %d out of range", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return xb_fail(nullptr, XB_ERR_UNSUPPORTED, "xb_create: device %d is not compute capability 10.x (sm_100a only)", device);
+    if (cudaSetDevice(device) != cudaSuccess) return xb_fail(nullptr, XB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    xb_handle *h = new xb_handle();
+    h->device = device;
+    h->max_N = max_N;
+    h->max_T = max_T;
+    h->n_base = n_base;
+    h->state_len = state_len;
+    h->C = ipow(n_base, state_len);
+    h->NZ = n_base + 1;
+    h->flags = flags;
+    h->bf16 = (flags & XB_FLAG_BF16) != 0;
+    h->num_sms = prop.multiProcessorCount;
+    strncpy(h->alphabet, alphabet, sizeof h->alphabet - 1);
+
+    const size_t TN = (size_t)max_T * max_N, S = (size_t)h->C * h->NZ;
+    int rc = XB_OK;
+#define TRY(x) if (rc == XB_OK) rc = (x)
+    TRY(dev_alloc(h, &h->alpha, (TN + max_N) * h->C));
+    TRY(dev_alloc(h, &h->bmax, (TN + max_N) * h->C));
+    TRY(dev_alloc(h, &h->lp, TN * S));
+    TRY(dev_alloc(h, &h->logz, (size_t)max_N));
+    TRY(dev_alloc(h, &h->seq_dev, TN));
+    TRY(dev_alloc(h, &h->lens_dev, (size_t)max_N));
+    if (!(flags & XB_FLAG_NO_ENCODER)) {
+        TRY(dev_alloc_bytes(h, &h->c2, TN * XB_CONV3_K * 2));
+        TRY(dev_alloc_bytes(h, &h->act0, TN * XB_FEATURES * 2));
+        TRY(dev_alloc_bytes(h, &h->act1, TN * XB_FEATURES * 2));
+        TRY(dev_alloc_bytes(h, &h->gates, TN * XB_GATES * 2));
+        TRY(dev_alloc(h, &h->cstate, (size_t)max_N * XB_FEATURES));
+        TRY(dev_alloc(h, &h->scores, TN * S));
+        TRY(dev_alloc_bytes(h, &h->signal_dev, TN * XB_STRIDE * sizeof(float)));
+    }
+#undef TRY
+    if (rc != XB_OK) {
+        xb_global_err = h->err;
+        xb_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return XB_OK;
+}
+
+int xb_destroy(xb_handle *h) {
+    if (!h) return XB_OK;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->conv1_w, h->conv1_b, h->conv2_w, h->conv2_b, h->conv3_w, h->conv3_b, h->head_w, h->head_b, h->c2,
+                    h->act0, h->act1, h->gates, h->cstate, h->hzero, h->scores, h->signal_dev, h->seq_dev, h->lens_dev,
+                    h->alpha, h->bmax, h->lp, h->logz, h->ctc_ws};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (auto &l : h->lstm) {
+        if (l.w_ih) cudaFree(l.w_ih);
+        if (l.w_hh) cudaFree(l.w_hh);
+        if (l.bias) cudaFree(l.bias);
+    }
+    delete h;
+    return XB_OK;
+}
+
+int xb_load_weights(xb_handle *h, const float *const *w, int n_tensors, float scale, float blank_score, int expand_blanks,
+                    void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "xb_load_weights: NULL handle");
+    XB_REQUIRE(h, !(h->flags & XB_FLAG_NO_ENCODER), "handle was created with XB_FLAG_NO_ENCODER");
+    XB_REQUIRE(h, w && n_tensors == XB_NUM_WEIGHTS, "expected %d weight tensors, got %d", XB_NUM_WEIGHTS, n_tensors);
+    for (int i = 0; i < n_tensors; i++) XB_REQUIRE(h, w[i] != nullptr, "weight tensor %d is NULL", i);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    XB_CUDA(h, cudaSetDevice(h->device));
+    const int F = XB_FEATURES;
+    h->head_rows = ipow(h->n_base, h->state_len + 1);
+    h->head_rows_padded = ((h->head_rows + 127) / 128) * 128;
+    if (!h->conv1_w) {
+        int rc = XB_OK;
+#define TRY(x) if (rc == XB_OK) rc = (x)
+        TRY(dev_alloc(h, &h->conv1_w, 20));
+        TRY(dev_alloc(h, &h->conv1_b, 4));
+        TRY(dev_alloc(h, &h->conv2_w, 320));
+        TRY(dev_alloc(h, &h->conv2_b, 16));
+        TRY(dev_alloc_bytes(h, &h->conv3_w, (size_t)F * XB_CONV3_K * 2));
+        TRY(dev_alloc(h, &h->conv3_b, (size_t)F));
+        for (auto &l : h->lstm) {
+            TRY(dev_alloc_bytes(h, &l.w_ih, (size_t)XB_GATES * F * 2));
+            TRY(dev_alloc_bytes(h, &l.w_hh, (size_t)XB_GATES * F * 2));
+            TRY(dev_alloc(h, &l.bias, (size_t)XB_GATES));
+        }
+        TRY(dev_alloc_bytes(h, &h->head_w, (size_t)h->head_rows_padded * F * 2));
+        TRY(dev_alloc(h, &h->head_b, (size_t)h->head_rows_padded));
+#undef TRY
+        if (rc != XB_OK) return rc;
+    }
+    XB_CUDA(h, cudaMemcpyAsync(h->conv1_w, w[0], 20 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv1_b, w[1], 4 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv2_w, w[2], 320 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv2_b, w[3], 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (int rc = repack(h, w[4], h->conv3_w, F, XB_CONV3_K, F, XB_C2_CH * XB_WINLEN, 2, s)) return rc;
+    XB_CUDA(h, cudaMemcpyAsync(h->conv3_b, w[5], F * 4, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < 5; l++) {
+        const float *const *lw = w + 6 + 4 * l;
+        if (int rc = repack(h, lw[0], h->lstm[l].w_ih, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
+        if (int rc = repack(h, lw[1], h->lstm[l].w_hh, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
+        lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(lw[2], lw[3], h->lstm[l].bias);
+        XB_LAUNCH_CHECK(h);
+    }
+    if (int rc = repack(h, w[26], h->head_w, h->head_rows_padded, F, h->head_rows, F, 0, s)) return rc;
+    XB_CUDA(h, cudaMemsetAsync(h->head_b, 0, (size_t)h->head_rows_padded * 4, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->head_b, w[27], (size_t)h->head_rows * 4, cudaMemcpyDeviceToDevice, s));
+    h->scale = scale;
+    h->blank_score = blank_score;
+    h->expand_blanks = expand_blanks;
+    h->weights_loaded = true;
+    return XB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ encoder
+int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, void *out_tnc, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
+    XB_REQUIRE(h, signal && out_tnc, "NULL buffer");
+    XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
+    const int T = L / XB_STRIDE;
+    if (int rc = check_tn(h, T, N)) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (int rc = xb_conv12_im2col(h, signal, sig_dtype, N, L, s)) return rc;
+    CUtensorMap tmA, tmB;
+    if (int rc = xb_make_tmap_2d(h, &tmA, h->c2, (uint64_t)N * T, XB_CONV3_K, XB_CONV3_K)) return rc;
+    if (int rc = xb_make_tmap_2d(h, &tmB, h->conv3_w, XB_FEATURES, XB_CONV3_K, XB_CONV3_K)) return rc;
+    GemmParams p;
+    p.M = N * T; p.N = XB_FEATURES; p.K = XB_CONV3_K;
+    p.bias = h->conv3_b; p.out = out_tnc; p.ldo = XB_FEATURES; p.T = T; p.NB = N;
+    return xb_gemm_launch(h, EPI_CONV3, tmA, tmB, p, s);
+}
+
+int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, int N, int reverse, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
+    XB_REQUIRE(h, layer >= 0 && layer < 5, "LSTM layer %d out of range", layer);
+    XB_REQUIRE(h, x_tnc && y_tnc && x_tnc != y_tnc, "x and y must be distinct non-NULL buffers");
+    if (int rc = check_tn(h, T, N)) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const xb_lstm_weights &lw = h->lstm[layer];
+    // (a) input projection for all time steps: gates (T*N, 3072) = x W_ih^T + (b_ih + b_hh)
+    {
+        CUtensorMap tmA, tmB;
+        if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+        if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_ih, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
+        GemmParams p;
+        p.M = T * N; p.N = XB_GATES; p.K = XB_FEATURES;
+        p.bias = lw.bias; p.out = h->gates; p.ldo = XB_GATES;
+        if (int rc = xb_gemm_launch(h, EPI_INPROJ, tmA, tmB, p, s)) return rc;
+    }
+    // (b) recurrence: one fused GEMM + cell kernel per time step; direction by indexing
+    CUtensorMap tmH, tmW;
+    if (int rc = xb_make_tmap_2d(h, &tmH, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+    if (int rc = xb_make_tmap_2d(h, &tmW, lw.w_hh, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
+    for (int i = 0; i < T; i++) {
+        const int t = reverse ? T - 1 - i : i;
+        const int tp = reverse ? t + 1 : t - 1;
+        GemmParams p;
+        p.M = N; p.N = XB_GATES; p.K = XB_FEATURES;
+        p.a_row_offset = (i == 0) ? 0 : tp * N;
+        p.out = y_tnc; p.NB = N;
+        p.gates = h->gates; p.cstate = h->cstate;
+        p.t_cur = t; p.first = (i == 0);
+        if (int rc = xb_gemm_launch(h, EPI_LSTM, tmH, tmW, p, s)) return rc;
+    }
+    return XB_OK;
+}
+
+int xb_lstm_stack_fwd(xb_handle *h, void *x_tnc, void *y_tnc, int T, int N, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, x_tnc && y_tnc && x_tnc != y_tnc, "x and y must be distinct non-NULL buffers");
+    // reverse, forward, reverse, forward, reverse (bonito/crf/model.py:152-154); ping-pong x -> y -> x -> y -> x -> y
+    void *a = x_tnc, *b = y_tnc;
+    for (int l = 0; l < 5; l++) {
+        if (int rc = xb_lstm_fwd(h, l, a, b, T, N, (l % 2) == 0, stream)) return rc;
+        void *t = a; a = b; b = t;
+    }
+    return XB_OK;   // 5 layers: result landed in y_tnc
+}
+
+int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
+    XB_REQUIRE(h, x_tnc && scores, "NULL buffer");
+    if (int rc = check_tn(h, T, N)) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmA, tmB;
+    if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+    if (int rc = xb_make_tmap_2d(h, &tmB, h->head_w, h->head_rows_padded, XB_FEATURES, XB_FEATURES)) return rc;
+    GemmParams p;
+    p.M = T * N; p.N = h->head_rows_padded; p.K = XB_FEATURES;
+    p.bias = h->head_b; p.out = scores;
+    p.ldo = h->expand_blanks ? h->C * h->NZ : h->head_rows;
+    p.n_base = h->n_base; p.head_rows = h->head_rows; p.expand = h->expand_blanks;
+    p.scale = h->scale; p.blank = h->blank_score;
+    return xb_gemm_launch(h, EPI_HEAD, tmA, tmB, p, s);
+}
+
+int xb_encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
+    const int T = L / XB_STRIDE;
+    if (int rc = xb_conv_stem_fwd(h, signal, sig_dtype, N, L, h->act0, stream)) return rc;
+    if (int rc = xb_lstm_stack_fwd(h, h->act0, h->act1, T, N, stream)) return rc;
+    return xb_crf_head_fwd(h, h->act1, scores, T, N, stream);
+}
+
+// ------------------------------------------------------------------------------------------ CRF
+#define XB_CRF_PROLOGUE()                                                        \
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");                  \
+    XB_REQUIRE(h, scores != nullptr, "scores is NULL");                          \
+    if (int rc_ = check_tn(h, T, N)) return rc_;                                 \
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream)
+
+int xb_crf_logz(xb_handle *h, const float *scores, int T, int N, float *logz, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, logz != nullptr, "logz is NULL");
+    return xb_decode_alpha(h, scores, T, N, nullptr, logz, s);
+}
+
+int xb_crf_forward_scores(xb_handle *h, const float *scores, int T, int N, float *alpha, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, alpha != nullptr, "alpha is NULL");
+    return xb_decode_alpha(h, scores, T, N, alpha, nullptr, s);
+}
+
+int xb_crf_backward_scores(xb_handle *h, const float *scores, int T, int N, float *beta, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, beta != nullptr, "beta is NULL");
+    return xb_decode_backward(h, scores, nullptr, T, N, nullptr, nullptr, nullptr, beta, 2, s);
+}
+
+int xb_crf_posteriors(xb_handle *h, const float *scores, int T, int N, float *post, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, post != nullptr, "post is NULL");
+    if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, nullptr, s)) return rc;
+    return xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, post, nullptr, 0, s);
+}
+
+int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labels_nt, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, labels_nt != nullptr, "labels is NULL");
+    if (int rc = xb_decode_backward(h, scores, nullptr, T, N, nullptr, h->bmax, nullptr, nullptr, 1, s)) return rc;
+    return xb_decode_viterbi_fwd(h, scores, h->bmax, T, N, labels_nt, nullptr, nullptr, nullptr, s);
+}
+
+int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring, int32_t *lens,
+                  int8_t *labels_nt, float *post, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, seq != nullptr && lens != nullptr, "seq / lens is NULL");
+    if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, nullptr, s)) return rc;
+    if (int rc = xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, post, nullptr, 0, s)) return rc;
+    return xb_decode_viterbi_fwd(h, h->lp, h->bmax, T, N, labels_nt, seq, qstring, lens, s);
+}
+
+int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                        const int32_t *lengths, int normalise, float *loss, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, targets && lengths && loss, "NULL buffer");
+    return xb_ctc_loss_impl(h, scores, T, N, targets, Lmax, lengths, normalise, loss, s);
+}
+
+int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
+              const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out, int out_stride,
+              int32_t *out_len, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, rows && chunk_first && chunk_count && read_len && out && out_len, "NULL buffer");
+    return xb_stitch_impl(h, rows, T, chunk_first, chunk_count, read_len, n_reads, chunksize, overlap, stride, out,
+                          out_stride, out_len, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L, int8_t *seq_host, int32_t *lens_host,
+                           void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, signal_host && seq_host && lens_host, "NULL buffer");
+    XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
+    const int T = L / XB_STRIDE;
+    if (int rc = check_tn(h, T, N)) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    XB_CUDA(h, cudaMemcpyAsync(h->signal_dev, signal_host, (size_t)N * L * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int rc = xb_encoder_fwd(h, h->signal_dev, XB_SIG_F32, N, L, h->scores, stream)) return rc;
+    if (int rc = xb_crf_decode(h, h->scores, T, N, h->seq_dev, nullptr, h->lens_dev, nullptr, nullptr, stream)) return rc;
+    XB_CUDA(h, cudaMemcpyAsync(seq_host, h->seq_dev, (size_t)N * T, cudaMemcpyDeviceToHost, s));
+    XB_CUDA(h, cudaMemcpyAsync(lens_host, h->lens_dev, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    XB_CUDA(h, cudaStreamSynchronize(s));
+    return XB_OK;
+}
+
+int xb_gemm_selftest(xb_handle *h, const void *A, const void *B, float *D, int M, int N, int K, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, A && B && D && M > 0 && N > 0 && K > 0, "bad GEMM arguments");
+    CUtensorMap tmA, tmB;
+    if (int rc = xb_make_tmap_2d(h, &tmA, A, M, K, K)) return rc;
+    if (int rc = xb_make_tmap_2d(h, &tmB, B, N, K, K)) return rc;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.out = D; p.ldo = N;
+    return xb_gemm_launch(h, EPI_F32, tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// Interface of gemm_tc.cu (tcgen05 GEMM with fused epilogues) to the rest of the library.
+#pragma once
+#include "xb_common.cuh"
+
+enum { EPI_F32 = 0, EPI_CONV3 = 1, EPI_INPROJ = 2, EPI_HEAD = 3, EPI_LSTM = 4 };
+
+struct GemmParams {
+    int M = 0, N = 0, K = 0;       // logical problem (rows of A that are valid, columns = rows of B, depth)
+    int a_row_offset = 0;          // added to the A row coordinate (LSTM: row block of h_{t-1})
+    const float *bias = nullptr;   // (N) fp32
+    void *out = nullptr;
+    int ldo = 0;                   // output row pitch in elements
+    int T = 0, NB = 0;             // conv3: rows are (chunk, t) -> stored at (t, chunk); LSTM: NB = batch
+    // head
+    int n_base = 0, head_rows = 0, expand = 0;
+    float scale = 0.f, blank = 0.f;
+    // lstm step
+    const void *gates = nullptr;   // (T, NB, 3072) 16-bit input projection (+bias)
+    float *cstate = nullptr;       // (NB, 768) fp32
+    int t_cur = 0, first = 0;
+};
+
+int xb_make_tmap_2d(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint64_t ld);
+int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p,
+                   cudaStream_t s);
