@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- signal samples/sec basecalled (sup@v3.3 XNA) on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp16|bf16]
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[1] = sup@v3.3 architecture,
+UB "X" alphabet (n_base 5), batch 512 x 4000-sample chunks: conv stem -> 5 LSTMs -> CRF head -> CRF
+posteriors -> max-marginal Viterbi -> left-packed base strings.  Metric (bonito/cli/basecaller.py:153-161):
+input signal samples consumed per second.
+
+  value   whole-job samples/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e     same metric through the host-buffer C-ABI call xb_compute_scores_host: pinned host signal in,
+          H2D + encoder + decode + D2H of packed strings inside the timed region
+  roofline  dominant kernel (LSTM recurrence, tensor-core bound): algorithmic FLOPs / CUDA-event time
+  cpu_baseline  the oracle's restatement of the reference CPU path, timed on this box's host cores on a
+          bounded sample (rank 0, N=1 only)
+
+--impl reference times the reference's own CPU implementation of the path (its torch modules as restated
+in oracle/bonito_oracle.py + the C CRF decode) on the host cores, same metric.
+Multi-GPU (torchrun): each rank runs the same batch shape on its own GPU (reads/chunks shard with no
+data-path collective -> weak scaling); NCCL only gathers the timing / counters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHABET = ['N', 'A', 'C', 'G', 'T', 'X']
+N_BASE, STATE_LEN, FEATURES = 5, 3, 768
+CHUNK, BATCH = 4000, 512
+T_STEPS = CHUNK // 5
+FLOP_PER_CHUNK = {   # SURVEY.md 8(d), 2*MAC
+    'conv': 2 * (4 * 1 * 5 * 4000 + 16 * 4 * 5 * 4000 + 768 * 16 * 19 * 800),
+    'lstm': 5 * 800 * 2 * (2 * 3072 * 768),
+    'head': 2 * 768 * 625 * 800,
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'tf_burst': p['bf16_tflops'], 'tf_sustained': p['bf16_tflops_sustained'],
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_reference_pass(n_chunks, threads, sd=None, repeats=1):
+    """One pass of the reference CPU path over n_chunks chunks: fp32 torch encoder (the reference's own
+    modules, restated) + CRF decode (C restatement) + left-pack.  Returns seconds per pass (best)."""
+    from oracle import bonito_oracle as bo
+    from oracle import cexact
+    torch.set_num_threads(threads)
+    if sd is None:
+        sd = bo.reference_state_dict(n_base=N_BASE, seed=25)
+    x = torch.randn(n_chunks, 1, CHUNK, generator=torch.Generator().manual_seed(1234))
+    best = float('inf')
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            scores = bo.encoder_forward(sd, x, N_BASE, library=True)
+        labels = cexact.crf_decode(scores.numpy(), N_BASE)
+        cexact.pack(labels, ALPHABET)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_chunks = 64                                     # = BASELINE.json configs[0]
+    cpu_reference_pass(4, cores)                      # warm-up (thread pools, page-in)
+    times = []
+    for _ in range(args.warmup):
+        cpu_reference_pass(n_chunks, cores)
+    for _ in range(args.steps):
+        times.append(cpu_reference_pass(n_chunks, cores))
+    total = sum(times)
+    value = n_chunks * CHUNK * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': 'signal samples/sec basecalled (sup@v3.3 XNA)', 'value': value, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'sup@v3.3 UB X (n_base 5), 4000-sample chunks, Viterbi decode; each step = a bounded '
+                               'sample of %d chunks of the %d-chunk batch on the host CPU' % (n_chunks, BATCH)},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d chunks x %d samples per step (torch fp32 encoder with all host threads + '
+                                   'C CRF decode, 1 thread)' % (n_chunks, CHUNK)},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from oracle import bonito_oracle as bo            # weights generator + cpu_baseline leg only
+    from xna_basecaller_b200._lib import Handle
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N, L, T = args.batch, CHUNK, T_STEPS
+    h = Handle(ALPHABET, STATE_LEN, max_N=N, max_T=T, device=dev, bf16=(args.dtype == 'bf16'))
+    sd = bo.reference_state_dict(n_base=N_BASE, seed=25)
+    h.load_weights(sd)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(N, L, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    seq_host = torch.empty(N, T, dtype=torch.int8).pin_memory()
+    lens_host = torch.empty(N, dtype=torch.int32).pin_memory()
+    scores = torch.empty(T, N, h.C * h.NZ, dtype=torch.float32, device=dev)
+
+    def step_device():
+        s = h.encoder(x_dev)
+        return h.decode(s, want_qstring=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    h.set_profiling(True)
+    h.stage_times()
+    launches0 = h.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = h.launches - launches0
+    stages = h.stage_times()
+    h.set_profiling(False)
+
+    # end to end through the host-buffer C-ABI call
+    for _ in range(2):
+        h.compute_scores_host(x_host, seq_host, lens_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.compute_scores_host(x_host, seq_host, lens_host)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.summary()
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = times.tolist()
+    samples_per_step = N * L * world
+    value = samples_per_step * args.steps / (dev_ms / 1e3)
+    e2e_value = samples_per_step * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        rec_ms, rec_spans = stages['lstm_recurrence']
+        # dominant kernel: the LSTM recurrence (one span = one layer = T recurrent steps of [N,768]x[768,3072])
+        flops_per_span = T * 2.0 * N * FEATURES * 4 * FEATURES
+        achieved = flops_per_span * rec_spans / (rec_ms / 1e3) / 1e12 if rec_ms > 0 else 0.0
+        line = {
+            'metric': 'signal samples/sec basecalled (sup@v3.3 XNA)', 'value': value, 'unit': 'samples/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: sup@v3.3 UB X (n_base 5), batch %d x %d-sample chunks per GPU, conv stem + '
+                                   '5 LSTM + CRF head + posteriors + Viterbi + left-pack; random-init weights; '
+                                   'per-step working set (activations 0.6 GB, scores 1.2 GB) exceeds the 126 MB L2, '
+                                   'no explicit flush' % (N, L),
+                       'batch_per_gpu': N, 'chunk': L, 'n_base': N_BASE, 'sharding': 'chunks across GPUs, no collective'},
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': N * L * 4 * world,
+                    'd2h_bytes_per_step': (N * T + N * 4) * world},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'tensor', 'kernel': 'lstm_recurrence', 'achieved': achieved, 'peak': pk['tf_sustained'],
+                         'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': None,
+                         'peak_source': pk['source'] + ', sustained figure (kernel timed inside a long step)'},
+            'stages_ms_per_step': {k: v[0] / args.steps for k, v in stages.items()},
+            'model_tflops': (sum(FLOP_PER_CHUNK.values()) * N * world) / (dev_ms / args.steps / 1e3) / 1e12,
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_chunks = 64                             # = BASELINE.json configs[0]
+            cpu_reference_pass(4, cores)
+            sec = cpu_reference_pass(n_chunks, cores, repeats=2)
+            line['cpu_baseline'] = {'value': n_chunks * L / sec, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                    'sample': '%d chunks x %d samples, best of 2 (torch fp32 encoder on all host '
+                                              'threads + C CRF decode on 1 thread)' % (n_chunks, L)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

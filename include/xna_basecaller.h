@@ -134,6 +134,15 @@ int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L,
 /* Introspection used by tests / bench: number of kernels this library launched on the handle so far. */
 int64_t xb_launch_count(const xb_handle *h);
 
+/* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * Stages: 0 conv1+conv2+im2col, 1 conv3 GEMM, 2 LSTM input-projection GEMMs, 3 LSTM recurrence,
+ * 4 CRF head GEMM, 5 CRF alpha sweep, 6 CRF backward sweep, 7 CRF Viterbi sweep + packing.
+ * xb_stage_times synchronises, adds the elapsed milliseconds and launch-span counts of every span
+ * recorded since the last call into ms[XB_NUM_STAGES] / spans[XB_NUM_STAGES], and clears them. */
+#define XB_NUM_STAGES 8
+int xb_set_profiling(xb_handle *h, int on);
+int xb_stage_times(xb_handle *h, float *ms, int *spans);
+
 /* Standalone tensor-core GEMM self-test hook: D (M,N) fp32 = A (M,K) x B (N,K)^T, 16-bit operands. */
 int xb_gemm_selftest(xb_handle *h, const void *A, const void *B, float *D, int M, int N, int K,
                      void *stream);

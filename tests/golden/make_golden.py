@@ -23,6 +23,9 @@ ALPHABETS = {4: ['N', 'A', 'C', 'G', 'T'], 5: ['N', 'A', 'C', 'G', 'T', 'X'],
              6: ['N', 'A', 'C', 'G', 'T', 'X', 'Y']}
 
 
+REF_SCALE = dict(head_gain=1.0, head_shift=0.0, wih_gain=1.0, whh_gain=1.0)
+
+
 def synthetic_scores(seed, T, N, n_base, state_len=3, blank=2.0):
     """SURVEY 8c golden (ii) / config 3: non-blank ~U(-5,5), blank column constant."""
     rs = np.random.RandomState(seed)
@@ -94,6 +97,13 @@ def main():
         enc[key + 'cs_sequence'] = cs['sequence'].numpy()
         enc[key + 'cs_qstring'] = cs['qstring'].numpy()
         enc[key + 'cs_moves'] = np.asarray(cs['moves'])
+    # reference-scale weights (unit gains, as the reference's own init): the <=1e-2 tolerance case
+    cfg = refshim.reference_config(ALPHABETS[5])
+    model = RM.Model(cfg).eval()
+    model.load_state_dict(bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE))
+    x = synthetic_signal(23, 2, 500)
+    with torch.no_grad():
+        enc['r5_scores'] = model(x).numpy()
     np.savez_compressed(os.path.join(OUT, 'encoder.npz'), **enc)
 
     # ---- (iv) chunk / stitch on index arrays

@@ -13,8 +13,9 @@ from oracle import bonito_oracle as bo
 
 pytestmark = pytest.mark.gpu
 
-SCORE_TOL_F16 = 1e-2
-SCORE_TOL_BF16 = 1.5e-1
+SCORE_TOL_F16 = 1e-2          # reference-scale weights (unit gains, like the reference's own init)
+SCORE_TOL_F16_AMPLIFIED = 6e-2  # test weights with a 12x head gain: fp16 weight rounding alone gives ~3e-2
+SCORE_TOL_BF16 = 5e-2           # bf16 operands at reference scale (8 mantissa bits: misses the 1e-2 bar)
 
 
 @pytest.fixture(scope='module')
@@ -84,7 +85,12 @@ def test_crf_head(enc5):
     got = h.crf_head(x.cuda()).cpu()
     assert got.shape == ref.shape
     assert torch.equal(got.view(50, 3, 125, 6)[..., 0], torch.full((50, 3, 125), 2.0))
-    assert (got - ref).abs().max().item() < 5e-3
+    # against the fp32 head: bounded by the fp16 rounding of the (12x amplified) head weights
+    assert (got - ref).abs().max().item() < SCORE_TOL_F16_AMPLIFIED
+    # against the same head evaluated on fp16-rounded weights: only accumulation order / tanh differ
+    sdq = dict(sd)
+    sdq['encoder.9.linear.weight'] = sd['encoder.9.linear.weight'].half().float()
+    assert (got - bo.crf_head(sdq, x.float(), 5)).abs().max().item() < 1e-3
 
 
 @pytest.mark.parametrize('n_base', [5, 6])
@@ -98,7 +104,7 @@ def test_encoder_scores_vs_reference_golden(golden, n_base):
     gold = torch.from_numpy(golden['encoder']['n%d_scores' % n_base])
     assert got.shape == gold.shape
     err = (got - gold).abs().max().item()
-    assert err <= SCORE_TOL_F16, err
+    assert err <= SCORE_TOL_F16_AMPLIFIED, err
     # decoded strings from the CUDA scores equal the reference's decode of its own fp32 scores
     seq, _, lens = h.decode(got, want_qstring=False)
     strings = [bytes(seq[i, :lens[i]].cpu().numpy().astype('u1')).decode() for i in range(2)]
@@ -106,10 +112,24 @@ def test_encoder_scores_vs_reference_golden(golden, n_base):
     h.close()
 
 
+def test_encoder_scores_reference_scale_tolerance(golden):
+    """The north-star tolerance: max abs error <= 1e-2 on the scores against the reference's fp32 output."""
+    from make_golden import REF_SCALE
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[5], 3, max_N=8, max_T=200)
+    h.load_weights(bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE))
+    got = h.encoder(synthetic_signal(23, 2, 500).cuda()).cpu()
+    err = (got - torch.from_numpy(golden['encoder']['r5_scores'])).abs().max().item()
+    print('fp16 max abs score error at reference scale', err)
+    assert err <= SCORE_TOL_F16, err
+    h.close()
+
+
 def test_encoder_bf16_option():
+    from make_golden import REF_SCALE
     from xna_basecaller_b200._lib import Handle
     h = Handle(ALPHABETS[5], 3, max_N=8, max_T=200, bf16=True)
-    sd = bo.reference_state_dict(n_base=5, seed=11)
+    sd = bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE)
     h.load_weights(sd)
     x = synthetic_signal(22, 3, 500)
     got = h.encoder(x.cuda()).cpu()

@@ -23,7 +23,10 @@ SYMBOLS = (
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
     'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+    'xb_set_profiling', 'xb_stage_times',
 )
+STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
+          'crf_backward', 'crf_viterbi')
 
 _lib = None
 
@@ -62,6 +65,8 @@ def load():
     lib.xb_launch_count.restype = ctypes.c_int64
     lib.xb_launch_count.argtypes = [vp]
     lib.xb_gemm_selftest.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    lib.xb_set_profiling.argtypes = [vp, ci]
+    lib.xb_stage_times.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         if name not in ('xb_last_error', 'xb_launch_count'):
             getattr(lib, name).restype = ci
@@ -121,6 +126,16 @@ class Handle:
     @property
     def launches(self):
         return int(self.lib.xb_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._check(self.lib.xb_set_profiling(self.h, int(on)), 'xb_set_profiling')
+
+    def stage_times(self):
+        """{stage: (milliseconds, spans)} accumulated since the last call (CUDA events on the launch stream)."""
+        ms = (ctypes.c_float * len(STAGES))()
+        n = (ctypes.c_int * len(STAGES))()
+        self._check(self.lib.xb_stage_times(self.h, ms, n), 'xb_stage_times')
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(STAGES)}
 
     # ------------------------------------------------------------------ weights / encoder
     def load_weights(self, state_dict, scale=5.0, blank_score=2.0, expand_blanks=True):

@@ -534,6 +534,7 @@ int vit_impl(xb_handle *h, const float *lp, const float *bmax, int T, int N, int
 }  // namespace
 
 int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s) {
+    xb_stage_timer tm(h, XB_ST_CRF_ALPHA, s);
 #define CALL(NB, SL) alpha_impl<NB, SL>(h, scores, T, N, alpha, logz, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL
@@ -543,6 +544,7 @@ int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alph
 // mode 1: Max-semiring backward scan of the raw scores into bmax;  mode 2: Log-semiring scan into beta
 int xb_decode_backward(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
                        float *post, float *beta, int mode, cudaStream_t s) {
+    xb_stage_timer tm(h, XB_ST_CRF_BACKWARD, s);
 #define CALL(NB, SL) backward_impl<NB, SL>(h, scores, alpha, T, N, lp, bmax, post, beta, mode, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL
@@ -550,6 +552,7 @@ int xb_decode_backward(xb_handle *h, const float *scores, const float *alpha, in
 
 int xb_decode_viterbi_fwd(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels,
                           int8_t *seq, int8_t *qstring, int32_t *lens, cudaStream_t s) {
+    xb_stage_timer tm(h, XB_ST_CRF_VITERBI, s);
 #define CALL(NB, SL) vit_impl<NB, SL>(h, lp, bmax, T, N, labels, seq, qstring, lens, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL

@@ -101,6 +101,29 @@ const char *xb_last_error(const xb_handle *h) { return h ? h->err.c_str() : xb_g
 
 int64_t xb_launch_count(const xb_handle *h) { return h ? h->launches : 0; }
 
+int xb_set_profiling(xb_handle *h, int on) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    h->profiling = on != 0;
+    return XB_OK;
+}
+
+int xb_stage_times(xb_handle *h, float *ms, int *spans) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, ms && spans, "NULL buffer");
+    for (int i = 0; i < XB_ST_COUNT; i++) { ms[i] = 0.f; spans[i] = 0; }
+    for (auto &sp : h->spans) {
+        XB_CUDA(h, cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        XB_CUDA(h, cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.stage] += t;
+        spans[sp.stage]++;
+        h->event_pool.push_back(sp.a);
+        h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+    return XB_OK;
+}
+
 int xb_create(xb_handle **out, int device, int max_N, int max_T, int n_base, int state_len, const char *alphabet, int flags) {
     if (!out) return xb_fail(nullptr, XB_ERR_ARG, "xb_create: out is NULL");
     *out = nullptr;
@@ -170,6 +193,8 @@ int xb_destroy(xb_handle *h) {
                     h->alpha, h->bmax, h->lp, h->logz, h->ctc_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto &l : h->lstm) {
         if (l.w_ih) cudaFree(l.w_ih);
         if (l.w_hh) cudaFree(l.w_hh);
@@ -241,7 +266,11 @@ int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int
     const int T = L / XB_STRIDE;
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (int rc = xb_conv12_im2col(h, signal, sig_dtype, N, L, s)) return rc;
+    {
+        xb_stage_timer tm(h, XB_ST_CONV12, s);
+        if (int rc = xb_conv12_im2col(h, signal, sig_dtype, N, L, s)) return rc;
+    }
+    xb_stage_timer tm(h, XB_ST_CONV3, s);
     CUtensorMap tmA, tmB;
     if (int rc = xb_make_tmap_2d(h, &tmA, h->c2, (uint64_t)N * T, XB_CONV3_K, XB_CONV3_K)) return rc;
     if (int rc = xb_make_tmap_2d(h, &tmB, h->conv3_w, XB_FEATURES, XB_CONV3_K, XB_CONV3_K)) return rc;
@@ -261,6 +290,7 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
     const xb_lstm_weights &lw = h->lstm[layer];
     // (a) input projection for all time steps: gates (T*N, 3072) = x W_ih^T + (b_ih + b_hh)
     {
+        xb_stage_timer tm(h, XB_ST_INPROJ, s);
         CUtensorMap tmA, tmB;
         if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
         if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_ih, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
@@ -270,6 +300,7 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
         if (int rc = xb_gemm_launch(h, EPI_INPROJ, tmA, tmB, p, s)) return rc;
     }
     // (b) recurrence: one fused GEMM + cell kernel per time step; direction by indexing
+    xb_stage_timer tm(h, XB_ST_LSTM_REC, s);
     CUtensorMap tmH, tmW;
     if (int rc = xb_make_tmap_2d(h, &tmH, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
     if (int rc = xb_make_tmap_2d(h, &tmW, lw.w_hh, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
@@ -305,6 +336,7 @@ int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N
     XB_REQUIRE(h, x_tnc && scores, "NULL buffer");
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    xb_stage_timer tm(h, XB_ST_HEAD, s);
     CUtensorMap tmA, tmB;
     if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
     if (int rc = xb_make_tmap_2d(h, &tmB, h->head_w, h->head_rows_padded, XB_FEATURES, XB_FEATURES)) return rc;

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/xna_basecaller.h"
 
@@ -25,8 +26,16 @@ struct xb_lstm_weights {
     float *bias = nullptr;       // (3072) fp32 = b_ih + b_hh, same row order
 };
 
+enum { XB_ST_CONV12 = 0, XB_ST_CONV3, XB_ST_INPROJ, XB_ST_LSTM_REC, XB_ST_HEAD, XB_ST_CRF_ALPHA, XB_ST_CRF_BACKWARD,
+       XB_ST_CRF_VITERBI, XB_ST_COUNT };
+
+struct xb_prof_span { int stage; cudaEvent_t a, b; };
+
 struct xb_handle {
     int device = 0;
+    bool profiling = false;
+    std::vector<xb_prof_span> spans;
+    std::vector<cudaEvent_t> event_pool;
     int max_N = 0, max_T = 0;
     int n_base = 0, state_len = 0, C = 0, NZ = 0;
     int flags = 0;
@@ -71,6 +80,21 @@ struct xb_handle {
 };
 
 extern thread_local std::string xb_global_err;
+
+// CUDA-event span around a stage on the launching stream (only when xb_set_profiling(h, 1))
+struct xb_stage_timer {
+    xb_handle *h; cudaStream_t s; int idx = -1;
+    xb_stage_timer(xb_handle *h_, int stage, cudaStream_t s_) : h(h_), s(s_) {
+        if (!h->profiling) return;
+        auto get = [&]() { cudaEvent_t e; if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+                           else cudaEventCreate(&e); return e; };
+        xb_prof_span sp{stage, get(), get()};
+        cudaEventRecord(sp.a, s);
+        h->spans.push_back(sp);
+        idx = (int)h->spans.size() - 1;
+    }
+    ~xb_stage_timer() { if (idx >= 0) cudaEventRecord(h->spans[idx].b, s); }
+};
 
 int xb_fail(xb_handle *h, int code, const char *fmt, ...);
 
