@@ -67,6 +67,25 @@ def test_lstm_layer(enc5, reverse):
     assert (got - ref).abs().max().item() < 4e-3
 
 
+@pytest.mark.parametrize('stepwise', [False, True])
+@pytest.mark.parametrize('N,T', [(100, 24), (200, 17), (577, 6)])
+def test_lstm_layer_multi_group(stepwise, N, T):
+    """Several batch groups per launch (96 chunks each), uneven last group, and more than one launch (N > 576)."""
+    from xna_basecaller_b200._lib import Handle
+    h = Handle(ALPHABETS[5], 3, max_N=N, max_T=T, lstm_stepwise=stepwise)
+    sd = bo.reference_state_dict(n_base=5, seed=11)
+    h.load_weights(sd)
+    g = torch.Generator().manual_seed(N + T)
+    x = (torch.randn(T, N, 768, generator=g) * 0.5).half()
+    p = 'encoder.5.rnn.'
+    for reverse in (False, True):
+        ref = bo.lstm_layer(x.float(), sd[p + 'weight_ih_l0'], sd[p + 'weight_hh_l0'], sd[p + 'bias_ih_l0'],
+                            sd[p + 'bias_hh_l0'], reverse)
+        got = h.lstm(1, x.cuda(), reverse).float().cpu()
+        assert (got - ref).abs().max().item() < 4e-3
+    h.close()
+
+
 def test_lstm_first_layer_golden(enc5, golden):
     """encoder.4 of the reference Model on the reference stem output."""
     h, sd = enc5

@@ -86,7 +86,8 @@ class Handle:
     """One xb_handle: a device, an alphabet, capacity (max_N chunks x max_T steps) and, after
     load_weights(), the repacked encoder weights."""
 
-    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True):
+    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True,
+                 lstm_stepwise=False):
         if not torch.cuda.is_available():
             raise RuntimeError('xna_basecaller_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = load()
@@ -99,7 +100,8 @@ class Handle:
         self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
         self.bf16 = bf16
         self.dtype16 = torch.bfloat16 if bf16 else torch.float16
-        flags = (XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
+        flags = ((XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
+                 | (XB_FLAG_LSTM_STEPWISE if lstm_stepwise else 0))
         h = ctypes.c_void_p()
         rc = self.lib.xb_create(ctypes.byref(h), self.device.index or 0, max_N, max_T, self.n_base, state_len,
                                 self.alphabet.encode(), flags)

@@ -242,6 +242,12 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 // 2-D K-major tensor map: rows x K 16-bit elements, row pitch ld elements, box 64 x 128, 128B swizzle.
 int xb_make_tmap_2d(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint64_t ld) {
+    return xb_make_tmap_2d_box(h, out, base, rows, K, ld, BK, BM, 1);
+}
+
+// general form: box_inner x box_rows elements; swizzle128 = 1 -> CU_TENSOR_MAP_SWIZZLE_128B (box_inner must be 64)
+int xb_make_tmap_2d_box(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint64_t ld,
+                        uint32_t box_inner, uint32_t box_rows, int swizzle128) {
     if (!h->encode_tiled) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -252,11 +258,12 @@ int xb_make_tmap_2d(xb_handle *h, CUtensorMap *out, const void *base, uint64_t r
     }
     cuuint64_t dims[2] = {K, rows};
     cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
         out, h->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims,
-        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return xb_fail(h, XB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return XB_OK;

@@ -20,6 +20,7 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 }
 
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
+int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
 int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
                      const int32_t *lengths, int normalise, float *loss, cudaStream_t s);
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
@@ -190,7 +191,7 @@ int xb_destroy(xb_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->conv1_w, h->conv1_b, h->conv2_w, h->conv2_b, h->conv3_w, h->conv3_b, h->head_w, h->head_b, h->c2,
                     h->act0, h->act1, h->gates, h->cstate, h->hzero, h->scores, h->signal_dev, h->seq_dev, h->lens_dev,
-                    h->alpha, h->bmax, h->lp, h->logz, h->ctc_ws};
+                    h->alpha, h->bmax, h->lp, h->logz, h->ctc_ws, h->lstm_counters};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -301,6 +302,7 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
     }
     // (b) recurrence: one fused GEMM + cell kernel per time step; direction by indexing
     xb_stage_timer tm(h, XB_ST_LSTM_REC, s);
+    if (!(h->flags & XB_FLAG_LSTM_STEPWISE)) return xb_lstm_recurrence_persistent(h, layer, y_tnc, T, N, reverse, s);
     CUtensorMap tmH, tmW;
     if (int rc = xb_make_tmap_2d(h, &tmH, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
     if (int rc = xb_make_tmap_2d(h, &tmW, lw.w_hh, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;

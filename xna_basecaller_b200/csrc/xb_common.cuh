@@ -74,6 +74,7 @@ struct xb_handle {
     float *lp = nullptr;         // (max_T, max_N, C*NZ)
     float *logz = nullptr;       // (max_N)
     float *ctc_ws = nullptr;
+    int *lstm_counters = nullptr; // per-group step counters of the persistent LSTM kernel
 
     // driver entry point for TMA descriptors (resolved at run time: no link-time libcuda dependency)
     void *encode_tiled = nullptr;
