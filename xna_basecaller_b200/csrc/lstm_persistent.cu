@@ -18,6 +18,8 @@
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11
 // epilogue (phase 1: TMEM -> +G -> fp32 scratch in smem, re-using the dead h buffer; phase 2: one thread
 // per (unit, chunk) cell with all four gates, no cross-lane exchange, 12 cells per thread).
+#include <stdlib.h>
+
 #include "xb_common.cuh"
 #include "xb_ptx.cuh"
 #include "xb_gemm.cuh"
@@ -48,7 +50,10 @@ struct PLParams {
     const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows
     uint16_t *y;                // (T, N, 768) 16-bit output = hidden states
     int *counters;              // (G) zeroed before launch
+    long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, steps 64..71
 };
+
+#define DBG(ev) do { if (p.dbg && blockIdx.x == 0 && s >= 64 && s < 72) p.dbg[(s - 64) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
@@ -131,14 +136,17 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 if (s > 0) {
                     const int tp = p.reverse ? t + 1 : t - 1;
                     const int need = TILES * s;
+                    DBG(0);
                     while (ld_acquire_gpu(p.counters + g) < need) {
                     }
+                    DBG(1);
                     fence_proxy_async_all();
 #pragma unroll 1
                     for (int kc = 0; kc < KCH; kc++) {
                         mbar_expect_tx(&h_full[kc], H_CHUNK_BYTES);
                         tma_load_2d(hbuf + kc * H_CHUNK_BYTES, &tmY, &h_full[kc], kc * 64, tp * N + b0);
                     }
+                    DBG(2);
                 }
                 if (s + 1 < T) {      // input projection of the next step, one step ahead
                     const int sn = s + 1, q = sn & 1, u = sn >> 1;
@@ -156,10 +164,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         for (int s = 1; s < T; s++) {
             mbar_wait(d_empty, (s - 1) & 1);          // epilogue of step s-1 has drained the accumulator
             tc_fence_after();
+            if (lane == 0) DBG(3);
 #pragma unroll 1
             for (int kc = 0; kc < KCH; kc++) {
                 mbar_wait(&h_full[kc], (s - 1) & 1);
                 tc_fence_after();
+                if (lane == 0 && kc == 0) DBG(4);
+                if (lane == 0 && kc == KCH - 1) DBG(5);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; k++)
@@ -170,6 +181,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             }
             if (elect_one()) mma_commit(d_full);
             __syncwarp();
+            if (lane == 0) DBG(6);
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (256 threads)
@@ -191,6 +203,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 mbar_wait(d_full, (s - 1) & 1);
                 tc_fence_after();
             }
+            if (et == 0) DBG(7);
             // phase 1: accumulator (+ G) -> fp32 scratch P[row][chunk]
 #pragma unroll
             for (int cc = 0; cc < 3; cc++) {
@@ -216,6 +229,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 mbar_arrive(&g_empty[s & 1]);
             }
             named_bar_sync(1, EPI_THREADS);
+            if (et == 0) DBG(8);
             // phase 2: cells (unit ul = 4e + ui, chunk b = lane + 32m)
 #pragma unroll
             for (int ui = 0; ui < 4; ui++) {
@@ -235,16 +249,20 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 }
             }
             named_bar_sync(1, EPI_THREADS);
+            if (et == 0) DBG(9);
             // coalesced store of the (chunks x 32 units) slice: 16 words per chunk row
             uint32_t *yrow = reinterpret_cast<uint32_t *>(p.y + ((size_t)t * N + b0) * XB_FEATURES + j * 32);
             for (int v = et; v < NB * 16; v += EPI_THREADS) {
                 const int b = v >> 4, wv = v & 15;
                 if (b < count) yrow[(size_t)b * (XB_FEATURES / 2) + wv] = HS[b * HS_STRIDE_W + wv];
             }
+            if (et == 0) DBG(10);
             __threadfence();
             fence_proxy_async_all();
             named_bar_sync(1, EPI_THREADS);
+            if (et == 0) DBG(11);
             if (et == 0) red_release_gpu_add(p.counters + g, 1);
+            if (et == 0) DBG(12);
         }
         tc_fence_before();
     }
@@ -257,11 +275,19 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 
 }  // namespace
 
+// debug: copy the timeline of the last launch (8 steps x 16 stamps) to the host
+extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
+    if (!h || !h->lstm_counters) return XB_ERR_STATE;
+    XB_CUDA(h, cudaDeviceSynchronize());
+    XB_CUDA(h, cudaMemcpy(out_host, h->lstm_counters + 16, 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return XB_OK;
+}
+
 // Recurrent part of one LSTM layer.  h->gates must already hold the input projection (T*N, 3072).
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
     if (!h->lstm_counters) {
         void *q = nullptr;
-        XB_CUDA(h, cudaMalloc(&q, 64 * sizeof(int)));
+        XB_CUDA(h, cudaMalloc(&q, 64 * sizeof(int) + 8 * 16 * sizeof(long long)));
         h->lstm_counters = reinterpret_cast<int *>(q);
     }
     CUtensorMap tmY, tmG;
@@ -278,7 +304,8 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
         p.w_hh = reinterpret_cast<const uint16_t *>(h->lstm[layer].w_hh);
         p.y = reinterpret_cast<uint16_t *>(y_tnc);
         p.counters = h->lstm_counters;
-        XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, 64 * sizeof(int), s));
+        p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + 16) : nullptr;
+        XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, 16 * sizeof(int), s));
         void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
         const void *fn = h->bf16 ? (const void *)lstm_persistent_kernel<true> : (const void *)lstm_persistent_kernel<false>;
         static bool configured[2] = {false, false};
