@@ -2,7 +2,7 @@
 import ctypes, os, sys
 os.environ['XB_LSTM_DEBUG'] = '1'
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import bonito_oracle as bo
 from xna_basecaller_b200._lib import Handle
 N, T = int(sys.argv[1]) if len(sys.argv) > 1 else 512, 200
@@ -16,7 +16,7 @@ buf = (ctypes.c_longlong * 128)()
 h.lib.xb_debug_lstm_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert h.lib.xb_debug_lstm_timeline(h.h, buf) == 0
 a = np.array(buf[:]).reshape(8, 16)
-names = ['poll_start', 'poll_done', 'tma_issued', 'mma_dempty', 'mma_h0', 'mma_h11', 'mma_commit', 'epi_dfull', 'epi_p1', 'epi_p2', 'epi_stored', 'epi_fenced', 'epi_red']
+names = ['poll_start', 'poll_done', 'tma_issued', 'mma_dempty', 'mma_hfull', 'mma_issued', 'mma_x', 'epi_dfull', 'epi_p1', 'epi_p2', 'epi_stored', 'epi_red']
 for s in range(1, 8):
     base = a[s, 0]
-    print('step', 64 + s, ' '.join('%s=%d' % (n, a[s, i] - base) for i, n in enumerate(names)), ' | step period', a[s, 0] - a[s - 1, 0])
+    print(os.environ.get('XB_LSTM_NO3D', '3d'), 'step', 64 + s, ' '.join('%s=%d' % (n, a[s, i] - base) for i, n in enumerate(names)), ' | step period', a[s, 0] - a[s - 1, 0])

@@ -44,7 +44,9 @@ int dev_alloc_bytes(xb_handle *h, void **p, size_t bytes) { return dev_alloc<uin
 // ---- weight repacking ------------------------------------------------------------------------------
 // dst (rows_dst, cols_dst) 16-bit <- src fp32; mode 0: plain rows (zero padding past rows_src / cols_src);
 // mode 1: LSTM gate interleave, dst row j*128 + g*32 + u <- src row g*768 + j*32 + u;
-// mode 2: conv3 (768,16,19) -> (768, 320) with column tap*16 + ch.
+// mode 2: conv3 (768,16,19) -> (768, 320) with column tap*16 + ch;
+// mode 3: LSTM unit-major interleave, dst row j*128 + u*4 + g <- src row g*768 + j*32 + u (the input projection
+//         of the persistent kernel: the four gates of a unit are adjacent in a row of G).
 template <bool BF16>
 __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restrict__ dst, int rows_dst, int cols_dst,
                               int rows_src, int cols_src, int mode) {
@@ -58,6 +60,9 @@ __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restric
     } else if (mode == 1) {
         int j = r >> 7, g = (r >> 5) & 3, u = r & 31;
         v = src[(size_t)(g * XB_FEATURES + j * 32 + u) * cols_src + c];
+    } else if (mode == 3) {
+        int j = r >> 7, u = (r >> 2) & 31, g = r & 3;
+        v = src[(size_t)(g * XB_FEATURES + j * 32 + u) * cols_src + c];
     } else {
         int tap = c >> 4, ch = c & 15;
         if (tap < XB_WINLEN) v = src[((size_t)r * XB_C2_CH + ch) * XB_WINLEN + tap];
@@ -65,10 +70,12 @@ __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restric
     typename X::T hv = X::from(v);
     dst[i] = *reinterpret_cast<uint16_t *>(&hv);
 }
-__global__ void lstm_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ dst) {
+__global__ void lstm_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ dst,
+                                 int mode) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= XB_GATES) return;
     int j = r >> 7, g = (r >> 5) & 3, u = r & 31;
+    if (mode == 3) { u = (r >> 2) & 31; g = r & 3; }
     int s = g * XB_FEATURES + j * 32 + u;
     dst[r] = b_ih[s] + b_hh[s];
 }
@@ -243,9 +250,10 @@ int xb_load_weights(xb_handle *h, const float *const *w, int n_tensors, float sc
     XB_CUDA(h, cudaMemcpyAsync(h->conv3_b, w[5], F * 4, cudaMemcpyDeviceToDevice, s));
     for (int l = 0; l < 5; l++) {
         const float *const *lw = w + 6 + 4 * l;
-        if (int rc = repack(h, lw[0], h->lstm[l].w_ih, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
+        const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
+        if (int rc = repack(h, lw[0], h->lstm[l].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
         if (int rc = repack(h, lw[1], h->lstm[l].w_hh, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
-        lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(lw[2], lw[3], h->lstm[l].bias);
+        lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(lw[2], lw[3], h->lstm[l].bias, ih_mode);
         XB_LAUNCH_CHECK(h);
     }
     if (int rc = repack(h, w[26], h->head_w, h->head_rows_padded, F, h->head_rows, F, 0, s)) return rc;
