@@ -71,6 +71,16 @@ int xb_destroy(xb_handle *h);
 int xb_load_weights(xb_handle *h, const float *const *tensors, int n_tensors, float scale,
                     float blank_score, int expand_blanks, void *stream);
 
+/* The same, one module at a time (what nn.Convolution x3 / nn.LSTM / nn.LinearCRFEncoder hold,
+ * nn.py:57-68,176-235,87-110), so that a single layer can be driven without the whole encoder.
+ * layer in 0..4 selects the weight slot xb_lstm_fwd reads; b (head bias) may be NULL. */
+int xb_load_conv_weights(xb_handle *h, const float *w1, const float *b1, const float *w2, const float *b2,
+                         const float *w3, const float *b3, void *stream);
+int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float *w_hh, const float *b_ih,
+                         const float *b_hh, void *stream);
+int xb_load_head_weights(xb_handle *h, const float *w, const float *b, float scale, float blank_score,
+                         int expand_blanks, void *stream);
+
 /* nn.Convolution x3 + nn.Permute([2,0,1]) (nn.py:57-68,156-167; crf/model.py:148-151).
  * signal (N, L) of sig_dtype -> out (T, N, 768) 16-bit. */
 int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, void *out_tnc,

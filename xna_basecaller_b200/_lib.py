@@ -19,7 +19,8 @@ NUM_WEIGHTS = 28
 
 # every symbol include/xna_basecaller.h declares (tests check that the library exports them all)
 SYMBOLS = (
-    'xb_abi_version', 'xb_last_error', 'xb_create', 'xb_destroy', 'xb_load_weights', 'xb_conv_stem_fwd',
+    'xb_abi_version', 'xb_last_error', 'xb_create', 'xb_destroy', 'xb_load_weights', 'xb_load_conv_weights',
+    'xb_load_lstm_weights', 'xb_load_head_weights', 'xb_conv_stem_fwd',
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
     'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
@@ -48,6 +49,9 @@ def load():
     lib.xb_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ctypes.c_char_p, ci]
     lib.xb_destroy.argtypes = [vp]
     lib.xb_load_weights.argtypes = [vp, ctypes.POINTER(vp), ci, cf, cf, ci, vp]
+    lib.xb_load_conv_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.xb_load_lstm_weights.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    lib.xb_load_head_weights.argtypes = [vp, vp, vp, cf, cf, ci, vp]
     lib.xb_conv_stem_fwd.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_lstm_fwd.argtypes = [vp, ci, vp, vp, ci, ci, ci, vp]
     lib.xb_lstm_stack_fwd.argtypes = [vp, vp, vp, ci, ci, vp]
@@ -155,6 +159,30 @@ class Handle:
                                       int(bool(expand_blanks) and blank_score is not None), _stream(self.device))
         self._check(rc, 'xb_load_weights')
         torch.cuda.current_stream(self.device).synchronize()   # tensors may be freed after this
+
+    def _f32(self, t):
+        return t.detach().to(self.device, torch.float32).contiguous()
+
+    def load_conv_weights(self, w1, b1, w2, b2, w3, b3):
+        ts = [self._f32(t) for t in (w1, b1, w2, b2, w3, b3)]
+        self._check(self.lib.xb_load_conv_weights(self.h, *[_ptr(t) for t in ts], _stream(self.device)),
+                    'xb_load_conv_weights')
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def load_lstm_weights(self, layer, w_ih, w_hh, b_ih, b_hh):
+        ts = [self._f32(t) for t in (w_ih, w_hh, b_ih, b_hh)]
+        self._check(self.lib.xb_load_lstm_weights(self.h, int(layer), *[_ptr(t) for t in ts], _stream(self.device)),
+                    'xb_load_lstm_weights')
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def load_head_weights(self, w, b, scale=5.0, blank_score=2.0, expand_blanks=True):
+        w = self._f32(w)
+        b = self._f32(b) if b is not None else None
+        self._check(self.lib.xb_load_head_weights(self.h, _ptr(w), _ptr(b), float(scale if scale is not None else 1.0),
+                                                  float(blank_score if blank_score is not None else 0.0),
+                                                  int(bool(expand_blanks) and blank_score is not None),
+                                                  _stream(self.device)), 'xb_load_head_weights')
+        torch.cuda.current_stream(self.device).synchronize()
 
     def _sig(self, signal):
         if signal.dim() == 3:

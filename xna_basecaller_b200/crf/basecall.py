@@ -1,0 +1,105 @@
+"""CRF basecalling with the reference's call surface (ub-bonito/bonito/crf/basecall.py): stitch_results
+(:15-24), compute_scores (:27-82, Viterbi branch), apply_stride_to_moves (:85-93), basecall (:96-119).
+
+compute_scores is one C-ABI call with HOST buffers (xb_compute_scores_host): pinned H2D of the chunk batch,
+fused stem, five persistent LSTM layers, CRF head, posteriors, max-marginal Viterbi and left-packing on the
+GPU, D2H of the packed (N, T) int8 letters and their lengths.  The Python loops of the reference (ord() per
+base, per-row padding) are gone; the returned dict has the same keys, dtypes and contents.
+"""
+import numpy as np
+import torch
+
+from ..multiprocessing import thread_iter
+from ..util import chunk, stitch, batchify, unbatchify
+
+
+def stitch_results(results, length, size, overlap, stride, reverse=False):
+    """Stitch results together with a given overlap."""
+    if isinstance(results, dict):
+        return {k: stitch_results(v, length, size, overlap, stride, reverse=reverse) for k, v in results.items()}
+    return stitch(results, size, overlap, length, stride, reverse=reverse)
+
+
+def _pinned(model, name, shape, dtype):
+    cache = model.__dict__.setdefault('_xb_pinned', {})
+    buf = cache.get(name)
+    if buf is None or buf.dtype != dtype or buf.numel() < int(np.prod(shape)):
+        buf = torch.empty(int(np.prod(shape)), dtype=dtype).pin_memory()
+        cache[name] = buf
+    return buf[:int(np.prod(shape))].view(*shape)
+
+
+def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offset=0.0, blank_score=2.0, reverse=False):
+    """Compute scores for model: batch (N, 1, chunksize) host tensor -> {'sequence', 'qstring', 'moves'}."""
+    head = model.encoder[-1]
+    if not head.expand_blanks:
+        raise RuntimeError('beam search (expand_blanks=False) is koi-only in the reference and is bypassed for UB '
+                           'alphabets (bonito/util.py:299-301); the B200 path decodes with Viterbi')
+    device = next(model.parameters()).device
+    N, _, L = batch.shape
+    T = L // model.stride
+    if reverse or batch.device.type != 'cpu':
+        # reverse complement permutes the score tensor between encoder and decode: two device calls
+        scores = model(batch.to(device))
+        if reverse:
+            scores = model.seqdist.reverse_complement(scores)
+        seq, qs, lens = model.seqdist.decode_packed(scores)
+        sequence, qstring = seq.cpu(), qs.cpu()
+    else:
+        eng = model.seqdist.engine
+        stem = model.encoder._stem()
+        if stem is None:
+            raise RuntimeError('compute_scores needs the sup@v3.3 encoder layout')
+        h = eng.get(device, N, T, bf16=next(model.parameters()).dtype == torch.bfloat16)
+        model.encoder.sync_weights(h)
+        staged = _pinned(model, 'signal', (N, L), torch.float32)
+        staged.copy_(batch[:, 0, :])
+        sequence = torch.empty(N, T, dtype=torch.int8)
+        lens = torch.empty(N, dtype=torch.int32)
+        seq_pin, lens_pin = _pinned(model, 'seq', (N, T), torch.int8), _pinned(model, 'lens', (N,), torch.int32)
+        h.compute_scores_host(staged, seq_pin, lens_pin)
+        sequence.copy_(seq_pin)
+        lens.copy_(lens_pin)
+        qstring = torch.where(sequence != 0, torch.tensor(ord('O'), dtype=torch.int8), torch.tensor(0, dtype=torch.int8))
+    return {
+        'qstring': qstring,
+        'sequence': sequence,
+        'moves': np.zeros((N, T), dtype=bool),
+    }
+
+
+def to_str(x):
+    """koi.decode.to_str as used by the reference: drop zeros, bytes -> ascii."""
+    x = np.asarray(x)
+    return x[x != 0].astype('u1').tobytes().decode('ascii')
+
+
+def apply_stride_to_moves(model, attrs):
+    moves = np.array(attrs['moves'], dtype=bool)
+    sig_move = np.full(moves.size * model.stride, False)
+    sig_move[np.where(moves)[0] * model.stride] = True
+    return {
+        'qstring': to_str(attrs['qstring']),
+        'sequence': to_str(attrs['sequence']),
+        'sig_move': sig_move,
+    }
+
+
+def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=False):
+    """Basecalls a set of reads: iterator of (read, {'sequence', 'qstring', 'sig_move'}) in input order."""
+    chunks = thread_iter(
+        ((read, 0, len(read.signal)), chunk(torch.from_numpy(read.signal), chunksize, overlap))
+        for read in reads
+    )
+    batches = thread_iter(batchify(chunks, batchsize=batchsize))
+    scores = thread_iter(
+        (read, compute_scores(model, batch, reverse=reverse)) for read, batch in batches
+    )
+    results = thread_iter(
+        (read, stitch_results(scores, end - start, chunksize, overlap, model.stride, reverse))
+        for ((read, start, end), scores) in unbatchify(scores)
+    )
+    return thread_iter(
+        (read, apply_stride_to_moves(model, attrs))
+        for read, attrs in results
+    )

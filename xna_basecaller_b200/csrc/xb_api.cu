@@ -212,64 +212,99 @@ int xb_destroy(xb_handle *h) {
     return XB_OK;
 }
 
-int xb_load_weights(xb_handle *h, const float *const *w, int n_tensors, float scale, float blank_score, int expand_blanks,
-                    void *stream) {
-    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "xb_load_weights: NULL handle");
-    XB_REQUIRE(h, !(h->flags & XB_FLAG_NO_ENCODER), "handle was created with XB_FLAG_NO_ENCODER");
-    XB_REQUIRE(h, w && n_tensors == XB_NUM_WEIGHTS, "expected %d weight tensors, got %d", XB_NUM_WEIGHTS, n_tensors);
-    for (int i = 0; i < n_tensors; i++) XB_REQUIRE(h, w[i] != nullptr, "weight tensor %d is NULL", i);
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    XB_CUDA(h, cudaSetDevice(h->device));
+static int alloc_weights(xb_handle *h) {
+    if (h->conv1_w) return XB_OK;
     const int F = XB_FEATURES;
     h->head_rows = ipow(h->n_base, h->state_len + 1);
     h->head_rows_padded = ((h->head_rows + 127) / 128) * 128;
-    if (!h->conv1_w) {
-        int rc = XB_OK;
+    int rc = XB_OK;
 #define TRY(x) if (rc == XB_OK) rc = (x)
-        TRY(dev_alloc(h, &h->conv1_w, 20));
-        TRY(dev_alloc(h, &h->conv1_b, 4));
-        TRY(dev_alloc(h, &h->conv2_w, 320));
-        TRY(dev_alloc(h, &h->conv2_b, 16));
-        TRY(dev_alloc_bytes(h, &h->conv3_w, (size_t)F * XB_CONV3_K * 2));
-        TRY(dev_alloc(h, &h->conv3_b, (size_t)F));
-        for (auto &l : h->lstm) {
-            TRY(dev_alloc_bytes(h, &l.w_ih, (size_t)XB_GATES * F * 2));
-            TRY(dev_alloc_bytes(h, &l.w_hh, (size_t)XB_GATES * F * 2));
-            TRY(dev_alloc(h, &l.bias, (size_t)XB_GATES));
-        }
-        TRY(dev_alloc_bytes(h, &h->head_w, (size_t)h->head_rows_padded * F * 2));
-        TRY(dev_alloc(h, &h->head_b, (size_t)h->head_rows_padded));
+    TRY(dev_alloc(h, &h->conv1_w, 20));
+    TRY(dev_alloc(h, &h->conv1_b, 4));
+    TRY(dev_alloc(h, &h->conv2_w, 320));
+    TRY(dev_alloc(h, &h->conv2_b, 16));
+    TRY(dev_alloc_bytes(h, &h->conv3_w, (size_t)F * XB_CONV3_K * 2));
+    TRY(dev_alloc(h, &h->conv3_b, (size_t)F));
+    for (auto &l : h->lstm) {
+        TRY(dev_alloc_bytes(h, &l.w_ih, (size_t)XB_GATES * F * 2));
+        TRY(dev_alloc_bytes(h, &l.w_hh, (size_t)XB_GATES * F * 2));
+        TRY(dev_alloc(h, &l.bias, (size_t)XB_GATES));
+    }
+    TRY(dev_alloc_bytes(h, &h->head_w, (size_t)h->head_rows_padded * F * 2));
+    TRY(dev_alloc(h, &h->head_b, (size_t)h->head_rows_padded));
 #undef TRY
-        if (rc != XB_OK) return rc;
-    }
-    XB_CUDA(h, cudaMemcpyAsync(h->conv1_w, w[0], 20 * 4, cudaMemcpyDeviceToDevice, s));
-    XB_CUDA(h, cudaMemcpyAsync(h->conv1_b, w[1], 4 * 4, cudaMemcpyDeviceToDevice, s));
-    XB_CUDA(h, cudaMemcpyAsync(h->conv2_w, w[2], 320 * 4, cudaMemcpyDeviceToDevice, s));
-    XB_CUDA(h, cudaMemcpyAsync(h->conv2_b, w[3], 16 * 4, cudaMemcpyDeviceToDevice, s));
-    if (int rc = repack(h, w[4], h->conv3_w, F, XB_CONV3_K, F, XB_C2_CH * XB_WINLEN, 2, s)) return rc;
-    XB_CUDA(h, cudaMemcpyAsync(h->conv3_b, w[5], F * 4, cudaMemcpyDeviceToDevice, s));
-    for (int l = 0; l < 5; l++) {
-        const float *const *lw = w + 6 + 4 * l;
-        const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
-        if (int rc = repack(h, lw[0], h->lstm[l].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
-        if (int rc = repack(h, lw[1], h->lstm[l].w_hh, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
-        lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(lw[2], lw[3], h->lstm[l].bias, ih_mode);
-        XB_LAUNCH_CHECK(h);
-    }
-    if (int rc = repack(h, w[26], h->head_w, h->head_rows_padded, F, h->head_rows, F, 0, s)) return rc;
+    return rc;
+}
+
+#define XB_WEIGHTS_PROLOGUE()                                                                          \
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");                                        \
+    XB_REQUIRE(h, !(h->flags & XB_FLAG_NO_ENCODER), "handle was created with XB_FLAG_NO_ENCODER");     \
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);                                           \
+    XB_CUDA(h, cudaSetDevice(h->device));                                                              \
+    if (int rc_ = alloc_weights(h)) return rc_
+
+int xb_load_conv_weights(xb_handle *h, const float *w1, const float *b1, const float *w2, const float *b2,
+                         const float *w3, const float *b3, void *stream) {
+    XB_WEIGHTS_PROLOGUE();
+    XB_REQUIRE(h, w1 && b1 && w2 && b2 && w3 && b3, "NULL convolution weight");
+    const int F = XB_FEATURES;
+    XB_CUDA(h, cudaMemcpyAsync(h->conv1_w, w1, 20 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv1_b, b1, 4 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv2_w, w2, 320 * 4, cudaMemcpyDeviceToDevice, s));
+    XB_CUDA(h, cudaMemcpyAsync(h->conv2_b, b2, 16 * 4, cudaMemcpyDeviceToDevice, s));
+    if (int rc = repack(h, w3, h->conv3_w, F, XB_CONV3_K, F, XB_C2_CH * XB_WINLEN, 2, s)) return rc;
+    XB_CUDA(h, cudaMemcpyAsync(h->conv3_b, b3, F * 4, cudaMemcpyDeviceToDevice, s));
+    h->loaded |= 1;
+    return XB_OK;
+}
+
+int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float *w_hh, const float *b_ih,
+                         const float *b_hh, void *stream) {
+    XB_WEIGHTS_PROLOGUE();
+    XB_REQUIRE(h, layer >= 0 && layer < 5, "LSTM layer %d out of range", layer);
+    XB_REQUIRE(h, w_ih && w_hh && b_ih && b_hh, "NULL LSTM weight");
+    const int F = XB_FEATURES;
+    const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
+    if (int rc = repack(h, w_ih, h->lstm[layer].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
+    if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
+    lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(b_ih, b_hh, h->lstm[layer].bias, ih_mode);
+    XB_LAUNCH_CHECK(h);
+    h->loaded |= 2 << layer;
+    return XB_OK;
+}
+
+int xb_load_head_weights(xb_handle *h, const float *w, const float *b, float scale, float blank_score,
+                         int expand_blanks, void *stream) {
+    XB_WEIGHTS_PROLOGUE();
+    XB_REQUIRE(h, w != nullptr, "NULL head weight");
+    const int F = XB_FEATURES;
+    if (int rc = repack(h, w, h->head_w, h->head_rows_padded, F, h->head_rows, F, 0, s)) return rc;
     XB_CUDA(h, cudaMemsetAsync(h->head_b, 0, (size_t)h->head_rows_padded * 4, s));
-    XB_CUDA(h, cudaMemcpyAsync(h->head_b, w[27], (size_t)h->head_rows * 4, cudaMemcpyDeviceToDevice, s));
+    if (b) XB_CUDA(h, cudaMemcpyAsync(h->head_b, b, (size_t)h->head_rows * 4, cudaMemcpyDeviceToDevice, s));
     h->scale = scale;
     h->blank_score = blank_score;
     h->expand_blanks = expand_blanks;
-    h->weights_loaded = true;
+    h->loaded |= 64;
     return XB_OK;
+}
+
+int xb_load_weights(xb_handle *h, const float *const *w, int n_tensors, float scale, float blank_score, int expand_blanks,
+                    void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "xb_load_weights: NULL handle");
+    XB_REQUIRE(h, w && n_tensors == XB_NUM_WEIGHTS, "expected %d weight tensors, got %d", XB_NUM_WEIGHTS, n_tensors);
+    for (int i = 0; i < n_tensors; i++) XB_REQUIRE(h, w[i] != nullptr, "weight tensor %d is NULL", i);
+    if (int rc = xb_load_conv_weights(h, w[0], w[1], w[2], w[3], w[4], w[5], stream)) return rc;
+    for (int l = 0; l < 5; l++) {
+        const float *const *lw = w + 6 + 4 * l;
+        if (int rc = xb_load_lstm_weights(h, l, lw[0], lw[1], lw[2], lw[3], stream)) return rc;
+    }
+    return xb_load_head_weights(h, w[26], w[27], scale, blank_score, expand_blanks, stream);
 }
 
 // ------------------------------------------------------------------------------------------ encoder
 int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, void *out_tnc, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
-    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
+    if (!(h->loaded & 1)) return xb_fail(h, XB_ERR_STATE, "convolution weights have not been loaded (xb_load_weights)");
     XB_REQUIRE(h, signal && out_tnc, "NULL buffer");
     XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
     const int T = L / XB_STRIDE;
@@ -291,8 +326,8 @@ int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int
 
 int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, int N, int reverse, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
-    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
     XB_REQUIRE(h, layer >= 0 && layer < 5, "LSTM layer %d out of range", layer);
+    if (!(h->loaded & (2 << layer))) return xb_fail(h, XB_ERR_STATE, "weights of LSTM layer %d have not been loaded", layer);
     XB_REQUIRE(h, x_tnc && y_tnc && x_tnc != y_tnc, "x and y must be distinct non-NULL buffers");
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -342,7 +377,7 @@ int xb_lstm_stack_fwd(xb_handle *h, void *x_tnc, void *y_tnc, int T, int N, void
 
 int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
-    if (!h->weights_loaded) return xb_fail(h, XB_ERR_STATE, "xb_load_weights has not been called");
+    if (!(h->loaded & 64)) return xb_fail(h, XB_ERR_STATE, "CRF head weights have not been loaded (xb_load_weights)");
     XB_REQUIRE(h, x_tnc && scores, "NULL buffer");
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

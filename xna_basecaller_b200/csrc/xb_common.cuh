@@ -40,7 +40,7 @@ struct xb_handle {
     int n_base = 0, state_len = 0, C = 0, NZ = 0;
     int flags = 0;
     bool bf16 = false;
-    bool weights_loaded = false;
+    int loaded = 0;              // bit 0 conv stem, bits 1..5 LSTM layers, bit 6 CRF head
     char alphabet[16] = {0};
     int num_sms = 0;
     int64_t launches = 0;
