@@ -1,0 +1,130 @@
+"""GPU tests of the drop-in plugin surface: the reference's own call sequence (load_symbol -> Model(config) ->
+load_state_dict -> .half().eval().to(device) -> basecall(model, reads, ...)) running on the CUDA path, checked
+against golden outputs of the reference code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from make_golden import ALPHABETS, synthetic_scores, synthetic_signal, synthetic_targets
+from oracle import bonito_oracle as bo
+from test_cpu_host import sup_config
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL_F16_AMPLIFIED = 6e-2   # same bound as tests/test_gpu_encoder.py for the gain-12 head of the golden weights
+
+
+@pytest.fixture(scope='module')
+def model5():
+    from xna_basecaller_b200 import util
+    cfg = sup_config(ALPHABETS[5])
+    Model = util.load_symbol(cfg, 'Model')
+    m = Model(cfg)
+    m.load_state_dict(bo.reference_state_dict(n_base=5, seed=11))
+    m = m.half().eval().to('cuda')
+    return m
+
+
+def test_model_forward_and_decode_batch(model5, golden):
+    x = synthetic_signal(21, 2, 500)
+    with torch.no_grad():
+        scores = model5(x.half().cuda())
+    gold = torch.from_numpy(golden['encoder']['n5_scores'])
+    assert scores.shape == gold.shape and scores.dtype == torch.float32
+    assert (scores.cpu() - gold).abs().max().item() <= SCORE_TOL_F16_AMPLIFIED
+    assert model5.decode_batch(scores) == list(golden['encoder']['n5_strings'])
+    assert model5.decode(scores[:, 0]) == str(golden['encoder']['n5_strings'][0])
+    assert model5.seqdist.engine.handle.launches > 0
+
+
+def test_layers_run_one_at_a_time(model5, golden):
+    """nn.LSTM / nn.LinearCRFEncoder called as stand-alone modules give the same result as the fused Serial."""
+    x = synthetic_signal(21, 2, 500).half().cuda()
+    enc = model5.encoder
+    with torch.no_grad():
+        y = enc[:4](x)                                   # fused stem -> (T, N, 768)
+        assert y.shape == (100, 2, 768)
+        stem_gold = torch.from_numpy(golden['encoder']['n5_stem_sub'])          # (N, 768/16, T)
+        assert (y.float().cpu().permute(1, 2, 0)[:, ::16, :] - stem_gold).abs().max().item() < 2e-2
+        for layer in enc[4:9]:
+            y = layer(y)
+        scores = enc[9](y)
+        whole = model5(x)
+    assert torch.equal(scores, whole)
+
+
+def test_compute_scores_matches_reference_golden(model5, golden):
+    from xna_basecaller_b200.crf.basecall import compute_scores
+    x = synthetic_signal(21, 2, 500)
+    out = compute_scores(model5, x)
+    g = golden['encoder']
+    assert out['sequence'].dtype == torch.int8 and out['qstring'].dtype == torch.int8 and out['moves'].dtype == bool
+    assert np.array_equal(out['sequence'].numpy(), g['n5_cs_sequence'])
+    assert np.array_equal(out['qstring'].numpy(), g['n5_cs_qstring'])
+    assert np.array_equal(out['moves'], g['n5_cs_moves'].astype(bool))
+
+
+def test_basecall_matches_reference_golden(model5, golden):
+    from xna_basecaller_b200 import util
+    g = golden['basecall']
+
+    class Read:
+        def __init__(self, rid, sig):
+            self.read_id, self.signal = rid, sig
+
+    rs = np.random.RandomState(77)
+    reads = [Read('read%d' % i, rs.randn(int(L)).astype(np.float32)) for i, L in enumerate(g['lengths'])]
+    basecall = util.load_symbol(model5.config, 'basecall')
+    out = list(basecall(model5, iter(reads), chunksize=1000, overlap=100, batchsize=4))
+    assert [r.read_id for r, _ in out] == [r.read_id for r in reads]
+    # (1) bit-exact against the oracle's decode + stitch of the SAME (CUDA) scores
+    crf = bo.CRF(3, ALPHABETS[5])
+
+    def score_fn(batch):
+        with torch.no_grad():
+            return model5(batch.cuda()).cpu()
+
+    want = dict(bo.basecall(score_fn, crf, [(r.read_id, r.signal) for r in reads], 1000, 100, 4))
+    same, worst = 0, 0
+    for rd, res in out:
+        assert set(res) == {'sequence', 'qstring', 'sig_move'}
+        assert res['sequence'] == want[rd.read_id]['sequence']
+        assert res['qstring'] == 'O' * len(res['sequence'])
+        assert len(res['sig_move']) == int(g[rd.read_id + '_sig_move_len']) and not res['sig_move'].any()
+        # (2) against the reference's own fp32 run: identical-read rate, differing reads must be near-ties
+        gold = str(g[rd.read_id + '_sequence'])
+        same += res['sequence'] == gold
+        worst = max(worst, _edit_distance(res['sequence'], gold))
+    print('identical-read rate vs the fp32 reference run: %d/%d, worst edit distance %d' % (same, len(reads), worst))
+    assert same >= len(reads) // 2 and worst <= 4
+
+
+def _edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[-1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def test_ctc_crf_methods(model5, golden):
+    sd = model5.seqdist
+    g = golden['crf']
+    s = synthetic_scores(0, 160, 3, 5).cuda()
+    np.testing.assert_allclose(sd.logZ(s).cpu().numpy(), g['n5_s0_logZ'], rtol=2e-6)
+    post = sd.posteriors(s)
+    assert np.abs(post[::9, :, ::7].cpu().numpy() - g['n5_s0_post_sub']).max() < 2e-5
+    assert np.array_equal(sd.viterbi(s).cpu().numpy().astype(np.int8), g['n5_s0_paths_raw'])
+    lp = (post + 1e-8).log()
+    paths = sd.viterbi(lp).to(torch.int16).T.cpu().numpy()
+    strings = [sd.path_to_str(p) for p in paths]
+    assert sum(a == b for a, b in zip(strings, g['n5_s0_strings'])) >= 2     # torch.log vs exact log: near-ties only
+    tg, tl = synthetic_targets(100, 3, 5, 30, 50)
+    loss = sd.ctc_loss(s, tg.cuda(), tl.cuda(), reduction='none')
+    np.testing.assert_allclose(loss.cpu().numpy(), g['n5_s0_ctc_loss'], rtol=1e-5)
+    assert abs(sd.ctc_loss(s, tg.cuda(), tl.cuda()).item() - g['n5_s0_ctc_loss'].mean()) < 1e-4
+    want = bo.CRF(3, ALPHABETS[5]).reverse_complement(s.cpu())
+    assert torch.equal(sd.reverse_complement(s).cpu(), want)
+    np.testing.assert_allclose((sd.normalise(s)).cpu().numpy(), bo.CRF(3, ALPHABETS[5]).normalise(s.cpu()).numpy(), atol=1e-4)
