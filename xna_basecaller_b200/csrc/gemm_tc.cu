@@ -270,15 +270,17 @@ int xb_make_tmap_2d_box(xb_handle *h, CUtensorMap *out, const void *base, uint64
 }
 
 // 3-D view of a (rows, 768) 16-bit activation matrix for the persistent LSTM: dims {64 k, rows, 12 k-blocks},
-// strides {1536 B, 128 B}, box {64, box_rows, 12}, 128B swizzle: one TMA lands 12 K-major [box_rows x 128 B] tiles.
-int xb_make_tmap_hview(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint32_t box_rows) {
+// strides {1536 B, 128 B}, box {64, box_rows, box_kblocks}, 128B swizzle: one TMA lands box_kblocks K-major
+// [box_rows x 128 B] tiles.
+int xb_make_tmap_hview(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint32_t box_rows,
+                       uint32_t box_kblocks) {
     if (!h->encode_tiled) {
         CUtensorMap tmp;
         if (int rc = xb_make_tmap_2d(h, &tmp, base, rows, XB_FEATURES, XB_FEATURES)) return rc;   // resolves the entry point
     }
     cuuint64_t dims[3] = {64, rows, XB_FEATURES / 64};
     cuuint64_t strides[2] = {XB_FEATURES * 2, 128};
-    cuuint32_t box[3] = {64, box_rows, XB_FEATURES / 64};
+    cuuint32_t box[3] = {64, box_rows, box_kblocks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
         out, h->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,

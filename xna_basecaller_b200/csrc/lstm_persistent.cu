@@ -3,24 +3,30 @@
 // initial state; a reversed layer walks time backwards by indexing instead of the reference's two flips).
 //
 // Decomposition.  W_hh (3072 x 768, 4.7 MB 16-bit) does not fit one SM, so it is cut into 24 tiles of 128 gate
-// rows = [i|f|g|o] x 32 hidden units (rows are permuted at weight-load time).  The batch is cut into G <= 6
-// groups of <= 96 chunks; CTA (g, j) owns tile j for group g, so 24*G <= 144 CTAs are resident, one per SM.
+// rows = 32 hidden units x [i,f,g,o] (rows are permuted at weight-load time: tile row = unit*4 + gate).  The
+// batch is cut into G <= 6 groups; CTA (g, j) owns tile j for group g, so 24*G <= 144 CTAs are resident, one
+// per SM.
 //   - the W_hh tile lives in TENSOR MEMORY for the whole kernel (128 lanes x 384 columns, the A operand of
 //     tcgen05.mma), loaded once with tcgen05.st;
-//   - a group is cut again into SUB = 3 sub-batches of <= 32 chunks that run the recurrence independently and
-//     out of phase: while one sub-batch waits for its h exchange, the tensor pipe and the epilogue warps work on
-//     the others (the serial chain of one step -- exchange through L2, TMA, MMA, cell update -- is ~3x longer
-//     than its tensor-pipe time);
-//   - per step and sub-batch the CTA loads h_{t-1} (32 x 768) with 12 TMA boxes (128B swizzle; the B operand),
-//     issues 48 tcgen05.mma (M=128 gate rows, N=32 chunks, K=16) into a 32-column fp32 accumulator in TMEM, adds
-//     the hoisted input projection G[t] (TMA-prefetched one step ahead), applies the cell update with the fp32
-//     cell state held in registers, and writes its 32-unit slice of h_t to HBM;
-//   - the 24 CTAs of a group exchange h_t through L2: release-add on a per-(group, sub-batch) counter,
-//     acquire-poll by the TMA producer, proxy fence, next TMA load.
+//   - a group is cut again into SUB sub-batches of <= NS chunks that run the recurrence independently and out
+//     of phase: the serial chain of one step (h exchange through L2, TMA, MMA, cell update) is several times
+//     longer than its tensor-pipe time, so the other sub-batches fill the pipe meanwhile;
+//   - per step and sub-batch the CTA loads h_{t-1} (NS x 768) with HP 3-D TMA boxes (128B swizzle; the B
+//     operand; the MMAs of a box start as soon as it lands), issues 48 tcgen05.mma (M=128 gate rows, N=NS
+//     chunks, K=16) into an NS-column fp32 accumulator in TMEM, adds the hoisted input projection G[t]
+//     (TMA-prefetched one step ahead), applies the cell update with the fp32 cell state held in registers, and
+//     writes its 32-unit slice of h_t to HBM;
+//   - the 24 CTAs of a group exchange h_t through L2: every epilogue warp release-adds a per-(group,
+//     sub-batch) counter after its stores, the TMA producer of the sub-batch acquire-polls it, proxy fence,
+//     next TMA load.  No CTA-wide barrier is on the per-step path.
 //
-// Warp roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..15 epilogue,
-// four per sub-batch (phase 1: TMEM -> fp32 scratch in smem, re-using the dead h buffer; phase 2: one thread per
-// (unit, chunk) cell with all four gates: lanes = 32 units, 8 chunks per thread).
+// Epilogue layout.  TMEM lane r = tile row = unit*4 + gate, so the four gates of a unit sit in four adjacent
+// lanes of one warp.  A warp reads its 32 lanes x NS columns with one tcgen05.ld, transposes 4x4 blocks with
+// two rounds of xor-shuffles (lane `gate` ends up with i,f,g,o of chunk 4i+gate), and each thread updates
+// NS/4 cells.  No shared-memory staging, no named barriers.
+//
+// Warp roles: warps 0..SUB-1 TMA producers (one per sub-batch: poll + loads), warp SUB MMA issuer + TMEM
+// allocator, epilogue warps start at the next multiple of four, four per sub-batch (warp % 4 = TMEM lane quarter).
 #include <stdlib.h>
 
 #include "xb_common.cuh"
@@ -31,34 +37,42 @@ using namespace xbptx;
 
 namespace {
 
-constexpr int SUB = 3;                     // sub-batches per group
-constexpr int NS = 32;                     // chunks (MMA N) per sub-batch
-constexpr int NB = SUB * NS;               // chunks per group
 constexpr int TILES = 24;                  // gate tiles per group
-constexpr int KCH = XB_FEATURES / 64;      // 12 K chunks of 64
-constexpr int H_CHUNK_BYTES = NS * 64 * 2; // 4096
-constexpr int H_BYTES = KCH * H_CHUNK_BYTES;        // 49152 per sub-batch
-constexpr int G_BYTES = NS * 128 * 2;               // 8192 per buffer
-constexpr int P_STRIDE = NS + 1;                    // fp32 scratch row stride (bank-conflict free)
-constexpr int HS_OFFSET = ((128 * P_STRIDE * 4 + 127) / 128) * 128;
-constexpr int NBAR = 8;                             // mbarriers per sub-batch
-constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + 1024 + 1024;
-constexpr int THREADS = 128 + SUB * 128;
-constexpr int D_COL = 384;                          // accumulators start after the 384 columns of W_hh
-static_assert(HS_OFFSET + NS * 64 <= H_BYTES, "epilogue scratch must fit in the h buffer");
-static_assert(D_COL + SUB * NS <= 512, "tensor memory columns");
+constexpr int KCH = XB_FEATURES / 64;      // 12 K blocks of 64
+constexpr int HP = 1;                      // h boxes per step (one 3-D box: several smaller boxes are served one after
+                                           // the other by the TMA unit, ~800 cycles each, and arrive later in total)
+constexpr int KPB = KCH / HP;              // K blocks per box
+constexpr int D_COL = 384;                 // accumulators start after the 384 columns of W_hh
+constexpr int CTR_STRIDE = 32;             // ints between counters (one 128-byte line each)
+constexpr int MAX_CTRS = 64;
+
+template <int SUB, int NS> struct Cfg {
+    static constexpr int NB = SUB * NS;                       // chunks per group
+    static constexpr int H_BLOCK_BYTES = NS * 64 * 2;         // one K block: NS rows x 128 B
+    static constexpr int H_PART_BYTES = KPB * H_BLOCK_BYTES;
+    static constexpr int H_BYTES = KCH * H_BLOCK_BYTES;
+    static constexpr int G_BYTES = NS * 128 * 2;
+    static constexpr int NBAR = HP + 1 + 4;                   // h_full[HP], d_full, g_full[2], g_empty[2]
+    static constexpr int EPI_WARP0 = ((SUB + 1 + 3) / 4) * 4;
+    static constexpr int THREADS = (EPI_WARP0 + 4 * SUB) * 32;
+    static constexpr int STAGE_BYTES = NS * 16;               // per epilogue warp: [chunk][8 units] 16-bit
+    static constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + SUB * 4 * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    static_assert(D_COL + SUB * NS <= 512, "tensor memory columns");
+    static_assert(NS % 16 == 0 && NS <= 32, "MMA N");
+    static_assert(SUB * NBAR * 8 + 16 <= 1024, "barrier block");
+    static_assert(H_BLOCK_BYTES % 1024 == 0, "swizzle atom alignment");
+};
 
 struct PLParams {
     int T, N, reverse;
     int batch0, nbatch, G;      // batch rows [batch0, batch0 + nbatch) are split into G groups
-    const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows (gate-major within a tile)
+    const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows (row = unit*4 + gate within a tile)
     uint16_t *y;                // (T, N, 768) 16-bit output = hidden states
-    int *counters;              // (G * SUB) zeroed before launch
-    int use3d;                  // tmY is the 3-D {k, chunk, k-block} view (one TMA per sub-batch step)
-    long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, steps 64..71
+    int *counters;              // G * SUB counters, CTR_STRIDE ints apart, zeroed before launch
+    long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
 };
 
-#define DBG(ev) do { if (p.dbg && blockIdx.x == 0 && s >= 64 && s < 72) p.dbg[(s - 64) * 16 + (ev)] = clock64(); } while (0)
+#define DBG(sub_, ev) do { if (p.dbg && blockIdx.x == 0 && s >= 64 && s < 72) p.dbg[((s - 64) * 8 + (sub_)) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
     float y;
@@ -72,41 +86,30 @@ __device__ __forceinline__ float rcpf(float x) {
 }
 __device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
 
-// c' = sig(f) c + sig(i) tanh(g);  h = sig(o) tanh(c').  Seven MUFU ops per cell: the four gate activations share
-// one reciprocal (1/(d_i d_f d_g d_o) times the complementary products); inputs are clamped so the product of the
-// four denominators stays far from fp32 overflow (sigmoid(-15) = 3e-7, tanh(7.5) = 1 - 6e-7).
-__device__ __forceinline__ float lstm_cell(float pi, float pf, float pg, float po, float &c) {
-    constexpr float L2E = 1.4426950408889634f;
-    const float ei = ex2f(-L2E * clampf(pi, 15.f)), ef = ex2f(-L2E * clampf(pf, 15.f));
-    const float eg = ex2f(-2.f * L2E * clampf(pg, 7.5f)), eo = ex2f(-L2E * clampf(po, 15.f));
-    const float di = 1.f + ei, df = 1.f + ef, dg = 1.f + eg, dq = 1.f + eo;
-    const float p1 = di * df, p2 = dg * dq;
-    const float r = rcpf(p1 * p2);
-    const float si = r * df * p2, sf = r * di * p2, so = r * p1 * dg, tg = (1.f - eg) * (r * p1 * dq);
-    const float cn = sf * c + si * tg;
-    c = cn;
-    const float ec = ex2f(-2.f * L2E * clampf(cn, 7.5f));
-    return so * (1.f - ec) * rcpf(1.f + ec);
-}
+template <int NS> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NS]);
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
 
-template <bool BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool BF16, int SUB, int NS>
+__global__ void __launch_bounds__(Cfg<SUB, NS>::THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
     using X = xb16<BF16>;
+    using C = Cfg<SUB, NS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *hbuf = smem;                                   // [SUB][H_BYTES]
-    uint8_t *gbuf = smem + SUB * H_BYTES;                   // [SUB][2][G_BYTES]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(gbuf + SUB * 2 * G_BYTES);
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + SUB * NBAR);
-    // per sub-batch: h_full, d_full, d_empty, g_full[2], g_empty[2]
-    auto h_full = [&](int sub) { return bars + sub * NBAR; };
-    auto d_full = [&](int sub) { return bars + sub * NBAR + 1; };
-    auto d_empty = [&](int sub) { return bars + sub * NBAR + 2; };
-    auto g_full = [&](int sub, int q) { return bars + sub * NBAR + 3 + q; };
-    auto g_empty = [&](int sub, int q) { return bars + sub * NBAR + 5 + q; };
+    uint8_t *hbuf = smem;                                       // [SUB][H_BYTES]
+    uint8_t *gbuf = smem + SUB * C::H_BYTES;                    // [SUB][2][G_BYTES]
+    uint8_t *stage = gbuf + SUB * 2 * C::G_BYTES;               // [SUB][4][STAGE_BYTES]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + SUB * 4 * C::STAGE_BYTES);
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + SUB * C::NBAR);
+    auto h_full = [&](int sub, int part) { return bars + sub * C::NBAR + part; };
+    auto d_full = [&](int sub) { return bars + sub * C::NBAR + HP; };
+    auto g_full = [&](int sub, int q) { return bars + sub * C::NBAR + HP + 1 + q; };
+    auto g_empty = [&](int sub, int q) { return bars + sub * C::NBAR + HP + 3 + q; };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are
+    // non-divergent and the epilogue shuffles need no re-convergence barriers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int g = blockIdx.x / TILES, j = blockIdx.x % TILES;
     const int T = p.T, N = p.N;
     const int b0 = p.batch0 + (int)(((long long)g * p.nbatch) / p.G);
@@ -117,12 +120,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY);
         prefetch_tmap(&tmG);
-    }
-    if (warp == 1 && lane == 0) {
         for (int sub = 0; sub < SUB; sub++) {
-            mbar_init(h_full(sub), 1);
+            for (int part = 0; part < HP; part++) mbar_init(h_full(sub, part), 1);
             mbar_init(d_full(sub), 1);
-            mbar_init(d_empty(sub), 4);
             for (int q = 0; q < 2; q++) {
                 mbar_init(g_full(sub, q), 1);
                 mbar_init(g_empty(sub, q), 4);
@@ -130,7 +130,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         }
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == SUB) {
         tmem_alloc(tmem_holder, 512);
         tmem_relinquish();
     }
@@ -139,8 +139,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    // W_hh tile -> tensor memory: lane = gate row of the tile, column c holds elements k = 2c, 2c+1
-    if (warp >= 4 && warp < 8) {
+    // W_hh tile -> tensor memory: lane = row of the tile, column c holds elements k = 2c, 2c+1
+    if (warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4) {
         const int q = warp & 3, r = q * 32 + lane;
         const uint4 *src = reinterpret_cast<const uint4 *>(p.w_hh + ((size_t)j * 128 + r) * XB_FEATURES);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -160,159 +160,229 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     __syncthreads();
     tc_fence_after();
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp < SUB) {
+        // ------------------------------------------------------------------ TMA producer of sub-batch `warp`
+        // (elect_one, not lane == 0: the compiler must see a single, warp-uniform issuer to keep TMA / MMA
+        // operands in uniform registers)
         if (elect_one()) {
-            const int t0 = p.reverse ? T - 1 : 0;
-            for (int sub = 0; sub < SUB; sub++) {
-                mbar_expect_tx(g_full(sub, 0), G_BYTES);
-                tma_load_2d(gbuf + (sub * 2) * G_BYTES, &tmG, g_full(sub, 0), j * 128, t0 * N + sub_row0(sub));
-            }
+            const int sub = warp;
+            const int row0 = sub_row0(sub);
+            const int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
+            uint8_t *hb = hbuf + sub * C::H_BYTES;
+            mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
+            tma_load_2d(gbuf + (sub * 2) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
             for (int s = 0; s < T; s++) {
                 const int t = p.reverse ? T - 1 - s : s;
-                for (int sub = 0; sub < SUB; sub++) {
-                    const int row0 = sub_row0(sub);
-                    if (s > 0) {
-                        const int tp = p.reverse ? t + 1 : t - 1;
-                        const int need = TILES * s;
-                        if (sub == 0) DBG(0);
-                        while (ld_acquire_gpu(p.counters + g * SUB + sub) < need) {
-                        }
-                        if (sub == 0) DBG(1);
-                        fence_proxy_async_global();
-                        // h_{t-1} of the sub-batch: ONE 3-D box {64 k, 32 chunks, 12 k-blocks} lands as 12 swizzled
-                        // [32 x 128 B] K-major tiles (per-box TMA latency, not bytes, dominated with 12 boxes)
-                        mbar_expect_tx(h_full(sub), H_BYTES);
-                        if (p.use3d) {
-                            tma_load_3d(hbuf + sub * H_BYTES, &tmY, h_full(sub), 0, tp * N + row0, 0);
-                        } else {
-#pragma unroll 1
-                            for (int kc = 0; kc < KCH; kc++)
-                                tma_load_2d(hbuf + sub * H_BYTES + kc * H_CHUNK_BYTES, &tmY, h_full(sub), kc * 64, tp * N + row0);
-                        }
-                        if (sub == 0) DBG(2);
+                if (s + 1 < T) {      // input projection of the next step, one step ahead
+                    const int sn = s + 1, q = sn & 1, u = sn >> 1;
+                    const int tn = p.reverse ? T - 1 - sn : sn;
+                    if (u >= 1) mbar_wait(g_empty(sub, q), (u - 1) & 1);
+                    mbar_expect_tx(g_full(sub, q), C::G_BYTES);
+                    tma_load_2d(gbuf + (sub * 2 + q) * C::G_BYTES, &tmG, g_full(sub, q), j * 128, tn * N + row0);
+                }
+                if (s > 0) {
+                    const int tp = p.reverse ? t + 1 : t - 1;
+                    const int need = TILES * 4 * s;          // every epilogue warp of the group has published step s-1
+                    DBG(sub, 0);
+                    while (ld_acquire_gpu(ctr) < need) {
                     }
-                    if (s + 1 < T) {      // input projection of the next step, one step ahead
-                        const int sn = s + 1, q = sn & 1, u = sn >> 1;
-                        const int tn = p.reverse ? T - 1 - sn : sn;
-                        if (u >= 1) mbar_wait(g_empty(sub, q), (u - 1) & 1);
-                        mbar_expect_tx(g_full(sub, q), G_BYTES);
-                        tma_load_2d(gbuf + (sub * 2 + q) * G_BYTES, &tmG, g_full(sub, q), j * 128, tn * N + row0);
+                    DBG(sub, 1);
+                    fence_proxy_async_global();
+                    // h_{t-1} of the sub-batch: HP boxes {64 k, NS chunks, KPB k-blocks}, each landing as KPB
+                    // swizzled [NS x 128 B] K-major tiles on its own mbarrier
+#pragma unroll
+                    for (int part = 0; part < HP; part++) {
+                        mbar_expect_tx(h_full(sub, part), C::H_PART_BYTES);
+                        tma_load_3d(hb + part * C::H_PART_BYTES, &tmY, h_full(sub, part), 0, tp * N + row0, part * KPB);
                     }
+                    DBG(sub, 2);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == SUB) {
+        // ------------------------------------------------------------------ MMA issuer: serve whichever sub-batch
+        // has its next h box in shared memory (no head-of-line blocking between the independent chains)
         constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, 128, NS);
         const uint32_t hb = smem_u32(hbuf);
-        for (int s = 1; s < T; s++) {
+        int step[SUB], part[SUB];
+#pragma unroll
+        for (int i = 0; i < SUB; i++) { step[i] = 1; part[i] = 0; }
+        int remaining = (T > 1) ? SUB : 0;
+        while (remaining > 0) {
+#pragma unroll
             for (int sub = 0; sub < SUB; sub++) {
-                mbar_wait(d_empty(sub), (s - 1) & 1);     // epilogue of step s-1 has drained this accumulator
+                if (step[sub] >= T) continue;
+                const int s = step[sub];
+                const int ready = mbar_test_wait(h_full(sub, part[sub]), (s - 1) & 1) ? 1 : 0;
+                if (!__shfl_sync(0xffffffffu, ready, 0)) continue;
                 tc_fence_after();
-                if (lane == 0 && sub == 0) DBG(3);
-                mbar_wait(h_full(sub), (s - 1) & 1);
-                tc_fence_after();
-                if (lane == 0 && sub == 0) DBG(4);
                 if (elect_one()) {
-                    const uint64_t bdesc0 = umma_desc_sw128(hb + sub * H_BYTES);
-#pragma unroll 4
-                    for (int kk = 0; kk < KCH * 4; kk++) {
+                    DBG(sub, 3 + 2 * part[sub]);
+                    const uint64_t bdesc0 = umma_desc_sw128(hb + sub * C::H_BYTES + part[sub] * C::H_PART_BYTES);
+                    const uint32_t a0 = tmem_base + part[sub] * (KPB * 32);
+                    const uint32_t d = tmem_base + D_COL + sub * NS;
+#pragma unroll
+                    for (int kk = 0; kk < KPB * 4; kk++) {
                         const int kc = kk >> 2, k = kk & 3;
-                        mma_f16_ts(tmem_base + D_COL + sub * NS, tmem_base + kk * 8,
-                                   bdesc0 + (uint64_t)((kc * H_CHUNK_BYTES + k * 32) >> 4), idesc, kk != 0);
+                        mma_f16_ts(d, a0 + kk * 8, bdesc0 + (uint64_t)((kc * C::H_BLOCK_BYTES + k * 32) >> 4), idesc,
+                                   (part[sub] | kk) != 0);
                     }
-                    mma_commit(d_full(sub));
+                    if (part[sub] == HP - 1) mma_commit(d_full(sub));
+                    DBG(sub, 4 + 2 * part[sub]);
                 }
                 __syncwarp();
-                if (lane == 0 && sub == 0) DBG(5);
-                if (lane == 0 && sub == 0) DBG(6);
+                if (++part[sub] == HP) {
+                    part[sub] = 0;
+                    if (++step[sub] >= T) remaining--;
+                }
             }
         }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (128 threads per sub-batch)
-        const int sub = (warp - 4) >> 2, q = warp & 3;
-        const int et = threadIdx.x - 128 - sub * 128;        // 0..127 within the sub-batch
-        const int r = q * 32 + lane;                         // gate row of the tile == TMEM lane
+    } else if (warp >= C::EPI_WARP0) {
+        // ------------------------------------------------------------------ epilogue (4 warps per sub-batch)
+        constexpr int CELLS = NS / 4;
+        const int sub = (warp - C::EPI_WARP0) >> 2, q = warp & 3;
+        const int gt = lane & 3, ul = lane >> 2;             // gate held after the TMEM load; unit within the warp
+        const int unit = q * 8 + ul;                         // unit within the tile
         const int row0 = sub_row0(sub);
         const int cnt = b0 + ((sub + 1) * count) / SUB - row0;   // valid chunks of this sub-batch (<= NS)
-        float *P = reinterpret_cast<float *>(hbuf + sub * H_BYTES);
-        uint16_t *HS = reinterpret_cast<uint16_t *>(hbuf + sub * H_BYTES + HS_OFFSET);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + D_COL + sub * NS;
-        const int bar_id = 1 + sub;
-        float cst[8];
+        int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
+        const bool bit0 = lane & 1, bit1 = lane & 2;
+        float cst[CELLS];
 #pragma unroll
-        for (int i = 0; i < 8; i++) cst[i] = 0.0f;
+        for (int i = 0; i < CELLS; i++) cst[i] = 0.0f;
 
         for (int s = 0; s < T; s++) {
             const int t = p.reverse ? T - 1 - s : s;
-            const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * 2 + (s & 1)) * G_BYTES);
+            const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * 2 + (s & 1)) * C::G_BYTES);
+            uint32_t acc[NS];
             if (s > 0) {
                 mbar_wait(d_full(sub), (s - 1) & 1);
                 tc_fence_after();
+                if (q == 0 && lane == 0) DBG(sub, 9);
+                tmem_ld_cols<NS>(taddr, acc);
+                tmem_ld_wait();
+                tc_fence_before();
+                if (q == 0 && lane == 0) DBG(sub, 10);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NS; i++) acc[i] = 0u;
             }
-            if (et == 0 && sub == 0) DBG(7);
-            // phase 1: accumulator -> fp32 scratch P[gate row][chunk]
-#pragma unroll
-            for (int cc = 0; cc < NS / 16; cc++) {
-                uint32_t acc[16];
-                if (s > 0) {
-                    tmem_ld_32x32b_x16(taddr + cc * 16, acc);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] = 0u;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i++) P[r * P_STRIDE + cc * 16 + i] = __uint_as_float(acc[i]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d_empty(sub));
             mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
-            named_bar_sync(bar_id, 128);
-            if (et == 0 && sub == 0) DBG(8);
-            // phase 2: cells (unit = lane, chunk b = q + 4m); G row b holds [unit][i,f,g,o] 16-bit
+            if (q == 0 && lane == 0) DBG(sub, 11);
+            // phase A: 4x4 transposes across the four lanes of a unit (lane `gt` ends with (i,f,g,o) of chunk 4i+gt);
+            // all blocks first so that the shuffles pipeline
+            float pre[CELLS][4];
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int b = q + 4 * m;
-                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + b * 128 + lane * 4);
+            for (int i = 0; i < CELLS; i++) {
+                float a0 = __uint_as_float(acc[4 * i]), a1 = __uint_as_float(acc[4 * i + 1]);
+                float a2 = __uint_as_float(acc[4 * i + 2]), a3 = __uint_as_float(acc[4 * i + 3]);
+                float r0 = __shfl_xor_sync(0xffffffffu, bit0 ? a0 : a1, 1);
+                float r1 = __shfl_xor_sync(0xffffffffu, bit0 ? a2 : a3, 1);
+                if (bit0) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
+                pre[i][0] = a0; pre[i][1] = a1; pre[i][2] = a2; pre[i][3] = a3;
+            }
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                float a0 = pre[i][0], a1 = pre[i][1], a2 = pre[i][2], a3 = pre[i][3];
+                float r0 = __shfl_xor_sync(0xffffffffu, bit1 ? a0 : a2, 2);
+                float r1 = __shfl_xor_sync(0xffffffffu, bit1 ? a1 : a3, 2);
+                if (bit1) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
+                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (4 * i + gt) * 128 + unit * 4);
                 const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
-                const float pi = P[(lane)*P_STRIDE + b] + g01.x;
-                const float pf = P[(32 + lane) * P_STRIDE + b] + g01.y;
-                const float pg = P[(64 + lane) * P_STRIDE + b] + g23.x;
-                const float po = P[(96 + lane) * P_STRIDE + b] + g23.y;
-                const float hn = lstm_cell(pi, pf, pg, po, cst[m]);
+                pre[i][0] = a0 + g01.x; pre[i][1] = a1 + g01.y; pre[i][2] = a2 + g23.x; pre[i][3] = a3 + g23.y;
+            }
+            // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
+            // that the MUFU latencies overlap.  Seven MUFU ops per cell: the four gate activations share one
+            // reciprocal (1/(d_i d_f d_g d_o) times the complementary products); inputs are clamped so that the
+            // product of the four denominators stays far from fp32 overflow (sigmoid(-15) = 3e-7, tanh(7.5) = 1 - 6e-7)
+            constexpr float L2E = 1.4426950408889634f;
+            float ei[CELLS], ef[CELLS], eg[CELLS], eo[CELLS], rr[CELLS];
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                ei[i] = ex2f(-L2E * clampf(pre[i][0], 15.f));
+                ef[i] = ex2f(-L2E * clampf(pre[i][1], 15.f));
+                eg[i] = ex2f(-2.f * L2E * clampf(pre[i][2], 7.5f));
+                eo[i] = ex2f(-L2E * clampf(pre[i][3], 15.f));
+            }
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                const float di = 1.f + ei[i], df = 1.f + ef[i], dg = 1.f + eg[i], dq = 1.f + eo[i];
+                const float p1 = di * df, p2 = dg * dq;
+                rr[i] = rcpf(p1 * p2);
+                // keep the partial products: sig(i) = r df p2, sig(f) = r di p2, sig(o) = r p1 dg, tanh(g) = (1-eg) r p1 dq
+                ei[i] = df * p2; ef[i] = di * p2; eo[i] = p1 * dg; eg[i] = (1.f - eg[i]) * (p1 * dq);
+            }
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                const float r = rr[i];
+                const float cn = (r * ef[i]) * cst[i] + (r * ei[i]) * (r * eg[i]);
+                cst[i] = cn;
+                eo[i] = r * eo[i];                             // sig(o)
+                ei[i] = ex2f(-2.f * L2E * clampf(cn, 7.5f));
+            }
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) rr[i] = rcpf(1.f + ei[i]);
+            // h slice of the warp (NS chunks x 8 units) through a 16 B-per-chunk staging row: one 16-byte global
+            // store per chunk instead of eight 2-byte ones
+            uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * 4 + q) * C::STAGE_BYTES));
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                const float hn = eo[i] * (1.f - ei[i]) * rr[i];
                 typename X::T hv = X::from(hn);
-                HS[b * 32 + lane] = *reinterpret_cast<uint16_t *>(&hv);
+                st[(4 * i + gt) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(g_empty(sub, s & 1));
-            named_bar_sync(bar_id, 128);
-            if (et == 0 && sub == 0) DBG(9);
-            // coalesced store of the (chunks x 32 units) slice: 64 bytes per chunk row
-            {
-                const int b = et >> 2, part = et & 3;
-                if (b < cnt)
-                    *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + b) * XB_FEATURES + j * 32 + part * 8) =
-                        reinterpret_cast<const uint4 *>(HS)[et];
-            }
-            fence_proxy_async();          // scratch (generic proxy) before the next TMA write into the same smem
-            named_bar_sync(bar_id, 128);
-            if (et == 0) {
-                if (sub == 0) DBG(10);
-                __threadfence();
-                red_release_gpu_add(p.counters + g * SUB + sub, 1);
-                if (sub == 0) DBG(11);
+            if (lane < NS && lane < cnt)
+                *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + lane) * XB_FEATURES + j * 32 + q * 8) =
+                    reinterpret_cast<const uint4 *>(st)[lane];
+            if (q == 0 && lane == 0) DBG(sub, 12);
+            __syncwarp();
+            if (lane == 0) {
+                red_release_gpu_add(ctr, 1);                  // publishes the warp's stores (cumulative over __syncwarp)
+                mbar_arrive(g_empty(sub, s & 1));
+                if (q == 0) DBG(sub, 13);
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == SUB) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+template <bool BF16, int SUB, int NS>
+int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
+    using C = Cfg<SUB, NS>;
+    CUtensorMap tmY, tmG;
+    if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
+    if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
+    const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
+    const int block_cap = max_groups * C::NB;
+    auto fn = lstm_persistent_kernel<BF16, SUB, NS>;
+    static bool configured = false;
+    if (!configured) {
+        XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    for (int batch0 = 0; batch0 < N; batch0 += block_cap) {
+        PLParams p;
+        p.T = T; p.N = N; p.reverse = reverse;
+        p.batch0 = batch0;
+        p.nbatch = (N - batch0 < block_cap) ? N - batch0 : block_cap;
+        p.G = (p.nbatch + C::NB - 1) / C::NB;
+        p.w_hh = reinterpret_cast<const uint16_t *>(h->lstm[layer].w_hh);
+        p.y = reinterpret_cast<uint16_t *>(y_tnc);
+        p.counters = h->lstm_counters;
+        p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE) : nullptr;
+        XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, MAX_CTRS * CTR_STRIDE * sizeof(int), s));
+        void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
+        XB_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, dim3(p.G * TILES), dim3(C::THREADS), args, C::SMEM_BYTES, s));
+        h->launches++;
+    }
+    return XB_OK;
 }
 
 }  // namespace
@@ -321,7 +391,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
     if (!h || !h->lstm_counters) return XB_ERR_STATE;
     XB_CUDA(h, cudaDeviceSynchronize());
-    XB_CUDA(h, cudaMemcpy(out_host, h->lstm_counters + 32, 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    XB_CUDA(h, cudaMemcpy(out_host, h->lstm_counters + MAX_CTRS * CTR_STRIDE, 8 * 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return XB_OK;
 }
 
@@ -330,38 +400,13 @@ extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
     if (!h->lstm_counters) {
         void *q = nullptr;
-        XB_CUDA(h, cudaMalloc(&q, 32 * sizeof(int) + 8 * 16 * sizeof(long long)));
+        XB_CUDA(h, cudaMalloc(&q, MAX_CTRS * CTR_STRIDE * sizeof(int) + 8 * 8 * 16 * sizeof(long long)));
         h->lstm_counters = reinterpret_cast<int *>(q);
     }
-    CUtensorMap tmY, tmG;
-    int use3d = getenv("XB_LSTM_NO3D") ? 0 : 1;
-    if (use3d && xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS) != XB_OK) use3d = 0;
-    if (!use3d)
-        if (int rc = xb_make_tmap_2d_box(h, &tmY, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES, 64, NS, 1)) return rc;
-    if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
-    const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
-    const int block_cap = max_groups * NB;
-    for (int batch0 = 0; batch0 < N; batch0 += block_cap) {
-        PLParams p;
-        p.T = T; p.N = N; p.reverse = reverse;
-        p.batch0 = batch0;
-        p.nbatch = (N - batch0 < block_cap) ? N - batch0 : block_cap;
-        p.G = (p.nbatch + NB - 1) / NB;
-        p.w_hh = reinterpret_cast<const uint16_t *>(h->lstm[layer].w_hh);
-        p.y = reinterpret_cast<uint16_t *>(y_tnc);
-        p.counters = h->lstm_counters;
-        p.use3d = use3d;
-        p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + 32) : nullptr;
-        XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, 32 * sizeof(int), s));
-        void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
-        const void *fn = h->bf16 ? (const void *)lstm_persistent_kernel<true> : (const void *)lstm_persistent_kernel<false>;
-        static bool configured[2] = {false, false};
-        if (!configured[h->bf16]) {
-            XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[h->bf16] = true;
-        }
-        XB_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(p.G * TILES), dim3(THREADS), args, SMEM_BYTES, s));
-        h->launches++;
-    }
-    return XB_OK;
+    static const int variant = getenv("XB_LSTM_VARIANT") ? atoi(getenv("XB_LSTM_VARIANT")) : 0;
+    if (variant == 1)
+        return h->bf16 ? launch_cfg<true, 6, 16>(h, layer, y_tnc, T, N, reverse, s)
+                       : launch_cfg<false, 6, 16>(h, layer, y_tnc, T, N, reverse, s);
+    return h->bf16 ? launch_cfg<true, 3, 32>(h, layer, y_tnc, T, N, reverse, s)
+                   : launch_cfg<false, 3, 32>(h, layer, y_tnc, T, N, reverse, s);
 }

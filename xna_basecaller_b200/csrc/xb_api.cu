@@ -266,7 +266,7 @@ int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float
     const int F = XB_FEATURES;
     const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
     if (int rc = repack(h, w_ih, h->lstm[layer].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
-    if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, 1, s)) return rc;
+    if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
     lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(b_ih, b_hh, h->lstm[layer].bias, ih_mode);
     XB_LAUNCH_CHECK(h);
     h->loaded |= 2 << layer;
