@@ -168,29 +168,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     *reinterpret_cast<uint4 *>(hout + ub) = hv;
                 }
             }
-        } else {
+        } else if constexpr (EPI == EPI_F32) {
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
                 uint32_t acc[32];
                 tmem_ld_32x32b_x32(taddr + cb, acc);
                 tmem_ld_wait();
                 const int nb = n0 + cb;
-                if (!row_ok) {
-                    // nothing to store for rows past M (the TMEM load above is warp-collective)
-                } else if constexpr (EPI == EPI_F32) {
+                if (row_ok) {
                     float *o = reinterpret_cast<float *>(p.out) + (size_t)m * p.ldo + nb;
 #pragma unroll
                     for (int j = 0; j < 32; j++)
                         if (nb + j < p.N) o[j] = __uint_as_float(acc[j]);
-                } else if constexpr (EPI == EPI_CONV3 || EPI == EPI_INPROJ) {
-                    size_t orow;
-                    if constexpr (EPI == EPI_CONV3) {
-                        const int b = m / p.T, t = m - b * p.T;       // im2col rows are (chunk, t)
-                        orow = (size_t)t * p.NB + b;
-                    } else {
-                        orow = (size_t)m;
-                    }
-                    uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldo + nb;
+                }
+            }
+        } else {
+            // Coalesced epilogues.  The accumulator arrives one tile ROW per thread; a direct store would touch 32
+            // different output rows per instruction.  Each epilogue warp therefore stages its 32 x 128 block in
+            // the (now idle: every MMA has completed) pipeline buffers and writes whole row segments.
+            uint8_t *stg = smem + q * (STAGES * STAGE_BYTES / 4);
+            if constexpr (EPI == EPI_CONV3 || EPI == EPI_INPROJ) {
+                constexpr int RSB = BN * 2 + 16;                 // staged row pitch in bytes (16 B pad: conflict free)
+#pragma unroll 1
+                for (int cb = 0; cb < BN; cb += 32) {
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(taddr + cb, acc);
+                    tmem_ld_wait();
+                    const int nb = n0 + cb;
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
@@ -202,26 +206,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         pk[j] = X::pack(v0, v1);
                     }
+                    uint4 *d = reinterpret_cast<uint4 *>(stg + r % 32 * RSB + cb * 2);
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        reinterpret_cast<uint4 *>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                } else if constexpr (EPI == EPI_HEAD) {
-                    float *o = reinterpret_cast<float *>(p.out) + (size_t)m * p.ldo;
+                    for (int j = 0; j < 4; j++) d[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                __syncwarp();
+                // 16 lanes x 16 B = one 256-byte row segment; two rows per instruction
+                const int half = lane >> 4, l16 = lane & 15;
 #pragma unroll 4
-                    for (int j = 0; j < 32; j++) {
-                        const int col = nb + j;
-                        if (col < p.head_rows) {
-                            float v = p.scale * fast_tanh(__uint_as_float(acc[j]) + __ldg(p.bias + col));
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int mm = m0 + q * 32 + rr + half;
+                    if (mm < p.M) {
+                        size_t orow;
+                        if constexpr (EPI == EPI_CONV3) {
+                            const int b = mm / p.T, t = mm - b * p.T;        // im2col rows are (chunk, t)
+                            orow = (size_t)t * p.NB + b;
+                        } else {
+                            orow = (size_t)mm;
+                        }
+                        uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldo + n0;
+                        reinterpret_cast<uint4 *>(o)[l16] = *reinterpret_cast<const uint4 *>(stg + (rr + half) * RSB + l16 * 16);
+                    }
+                }
+            } else {   // EPI_HEAD
+                constexpr int RS = 161;                          // staged row pitch in floats (odd: conflict free)
+                float *S = reinterpret_cast<float *>(stg);
+                const int nbs = p.n_base;
+                const int col_end = min(n0 + BN, p.head_rows);   // head columns of this tile: [n0, col_end)
+                int seg_start, seg_len;
+                if (p.expand) {
+                    seg_start = n0 + n0 / nbs + ((n0 % nbs) ? 1 : 0);
+                    seg_len = (col_end - 1) + (col_end - 1) / nbs + 2 - seg_start;
+                } else {
+                    seg_start = n0;
+                    seg_len = col_end - n0;
+                }
+#pragma unroll 1
+                for (int cb = 0; cb < BN; cb += 32) {
+                    if (n0 + cb >= col_end) break;
+                    uint32_t acc[32];
+                    tmem_ld_32x32b_x32(taddr + cb, acc);
+                    tmem_ld_wait();
+                    int col = n0 + cb, c = col / nbs, e = col - c * nbs;
+                    float *Sr = S + (r % 32) * RS;
+#pragma unroll
+                    for (int j = 0; j < 32; j++, col++) {
+                        if (col < col_end) {
+                            const float v = p.scale * fast_tanh(__uint_as_float(acc[j]) + __ldg(p.bias + col));
                             if (p.expand) {
-                                const int c = col / p.n_base, e = col - c * p.n_base;
-                                float *dst = o + c * (p.n_base + 1);
-                                if (e == 0) dst[0] = p.blank;
-                                dst[1 + e] = v;
+                                const int o = col + c + 1 - seg_start;
+                                if (e == 0) Sr[o - 1] = p.blank;
+                                Sr[o] = v;
+                                if (++e == nbs) { e = 0; c++; }
                             } else {
-                                o[col] = v;
+                                Sr[col - seg_start] = v;
                             }
                         }
                     }
+                }
+                __syncwarp();
+                float *obase = reinterpret_cast<float *>(p.out) + seg_start;
+#pragma unroll 1
+                for (int rr = 0; rr < 32; rr++) {
+                    const int mm = m0 + q * 32 + rr;
+                    if (mm >= p.M) break;
+                    float *o = obase + (size_t)mm * p.ldo;
+                    const float *Sr = S + rr * RS;
+                    for (int idx = lane; idx < seg_len; idx += 32) o[idx] = Sr[idx];
                 }
             }
         }
