@@ -98,7 +98,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
+    }
+    // Epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows).  The fused LSTM step keeps its four dedicated
+    // warps; every other epilogue runs on all eight warps (the producer / MMA warps are idle once the main loop has
+    // been issued): warps 0-3 take tile columns 0..63, warps 4-7 columns 64..127.  (EPI_F32, the self test, also keeps four.)
+    __syncwarp();
+    if ((EPI == EPI_LSTM || EPI == EPI_F32) ? warp >= 4 : true) {
         const int q = warp & 3;
         const int r = q * 32 + lane;             // tile row == TMEM lane
         const int m = m0 + r;
@@ -186,11 +191,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // Coalesced epilogues.  The accumulator arrives one tile ROW per thread; a direct store would touch 32
             // different output rows per instruction.  Each epilogue warp therefore stages its 32 x 128 block in
             // the (now idle: every MMA has completed) pipeline buffers and writes whole row segments.
-            uint8_t *stg = smem + q * (STAGES * STAGE_BYTES / 4);
+            uint8_t *stg = smem + warp * (STAGES * STAGE_BYTES / 8);
+            constexpr int HN = BN / 2;                           // columns per warp
+            const int c0 = (warp >> 2) * HN;                     // first tile column of this warp
             if constexpr (EPI == EPI_CONV3 || EPI == EPI_INPROJ) {
-                constexpr int RSB = BN * 2 + 16;                 // staged row pitch in bytes (16 B pad: conflict free)
+                constexpr int RSB = HN * 2 + 16;                 // staged row pitch in bytes (16 B pad: conflict free)
 #pragma unroll 1
-                for (int cb = 0; cb < BN; cb += 32) {
+                for (int cb = c0; cb < c0 + HN; cb += 32) {
                     uint32_t acc[32];
                     tmem_ld_32x32b_x32(taddr + cb, acc);
                     tmem_ld_wait();
@@ -206,15 +213,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         pk[j] = X::pack(v0, v1);
                     }
-                    uint4 *d = reinterpret_cast<uint4 *>(stg + r % 32 * RSB + cb * 2);
+                    uint4 *d = reinterpret_cast<uint4 *>(stg + lane * RSB + (cb - c0) * 2);
 #pragma unroll
                     for (int j = 0; j < 4; j++) d[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
                 __syncwarp();
-                // 16 lanes x 16 B = one 256-byte row segment; two rows per instruction
-                const int half = lane >> 4, l16 = lane & 15;
+                // 8 lanes x 16 B = one 128-byte row segment; four rows per instruction
+                const int half = lane >> 3, l16 = lane & 7;
 #pragma unroll 4
-                for (int rr = 0; rr < 32; rr += 2) {
+                for (int rr = 0; rr < 32; rr += 4) {
                     const int mm = m0 + q * 32 + rr + half;
                     if (mm < p.M) {
                         size_t orow;
@@ -224,31 +231,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
                             orow = (size_t)mm;
                         }
-                        uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldo + n0;
+                        uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldo + n0 + c0;
                         reinterpret_cast<uint4 *>(o)[l16] = *reinterpret_cast<const uint4 *>(stg + (rr + half) * RSB + l16 * 16);
                     }
                 }
             } else {   // EPI_HEAD
-                constexpr int RS = 161;                          // staged row pitch in floats (odd: conflict free)
+                constexpr int RS = 81;                           // staged row pitch in floats (odd: conflict free)
                 float *S = reinterpret_cast<float *>(stg);
                 const int nbs = p.n_base;
-                const int col_end = min(n0 + BN, p.head_rows);   // head columns of this tile: [n0, col_end)
-                int seg_start, seg_len;
-                if (p.expand) {
-                    seg_start = n0 + n0 / nbs + ((n0 % nbs) ? 1 : 0);
-                    seg_len = (col_end - 1) + (col_end - 1) / nbs + 2 - seg_start;
-                } else {
-                    seg_start = n0;
-                    seg_len = col_end - n0;
+                const int col0 = n0 + c0;                        // head columns of this warp: [col0, col_end)
+                const int col_end = min(col0 + HN, p.head_rows);
+                int seg_start = 0, seg_len = 0;
+                if (col_end > col0) {
+                    if (p.expand) {
+                        seg_start = col0 + col0 / nbs + ((col0 % nbs) ? 1 : 0);
+                        seg_len = (col_end - 1) + (col_end - 1) / nbs + 2 - seg_start;
+                    } else {
+                        seg_start = col0;
+                        seg_len = col_end - col0;
+                    }
                 }
 #pragma unroll 1
-                for (int cb = 0; cb < BN; cb += 32) {
+                for (int cb = c0; cb < c0 + HN; cb += 32) {
                     if (n0 + cb >= col_end) break;
                     uint32_t acc[32];
                     tmem_ld_32x32b_x32(taddr + cb, acc);
                     tmem_ld_wait();
                     int col = n0 + cb, c = col / nbs, e = col - c * nbs;
-                    float *Sr = S + (r % 32) * RS;
+                    float *Sr = S + lane * RS;
 #pragma unroll
                     for (int j = 0; j < 32; j++, col++) {
                         if (col < col_end) {
