@@ -92,6 +92,14 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
+def workload_config(N, L):
+    return {'workload': 'configs[1]: sup@v3.3 UB X (n_base 5), batch %d x %d-sample chunks per GPU, conv stem + '
+                        '5 LSTM + CRF head + posteriors + Viterbi + left-pack; random-init weights; '
+                        'per-step working set (activations 0.6 GB, gates 2.5 GB, scores 1.2 GB) exceeds the 126 MB L2, '
+                        'no explicit flush' % (N, L),
+            'batch_per_gpu': N, 'chunk': L, 'n_base': N_BASE, 'sharding': 'chunks across GPUs, no collective'}
+
+
 def cpu_reference_pass(n_chunks, threads, sd=None, repeats=1):
     """One pass of the reference CPU path over n_chunks chunks: fp32 torch encoder (the reference's own
     modules, restated) + CRF decode (C restatement) + left-pack.  Returns seconds per pass (best)."""
@@ -106,7 +114,7 @@ def cpu_reference_pass(n_chunks, threads, sd=None, repeats=1):
         t0 = time.perf_counter()
         with torch.no_grad():
             scores = bo.encoder_forward(sd, x, N_BASE, library=True)
-        labels = cexact.crf_decode(scores.numpy(), N_BASE)
+        labels = cexact.crf_decode_threads(scores.numpy(), N_BASE, threads=threads)
         cexact.pack(labels, ALPHABET)
         best = min(best, time.perf_counter() - t0)
     return best
@@ -129,11 +137,11 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'signal samples/sec basecalled (sup@v3.3 XNA)', 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'sup@v3.3 UB X (n_base 5), 4000-sample chunks, Viterbi decode; each step = a bounded '
-                               'sample of %d chunks of the %d-chunk batch on the host CPU' % (n_chunks, BATCH)},
+        'config': dict(workload_config(args.batch, CHUNK), sample='each step = %d chunks of the %d-chunk batch on the '
+                                                                  'host CPU' % (n_chunks, args.batch)),
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d chunks x %d samples per step (torch fp32 encoder with all host threads + '
-                                   'C CRF decode, 1 thread)' % (n_chunks, CHUNK)},
+                         'sample': '%d chunks x %d samples per step (torch fp32 encoder + C CRF decode, both on all '
+                                   '%d host threads)' % (n_chunks, CHUNK, cores)},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -231,21 +239,44 @@ def main():
         # dominant kernel: the LSTM recurrence (one span = one layer = T recurrent steps of [N,768]x[768,3072])
         flops_per_span = T * 2.0 * N * FEATURES * 4 * FEATURES
         achieved = flops_per_span * rec_spans / (rec_ms / 1e3) / 1e12 if rec_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get('lstm_persistent_kernel', {}).get('dram_bytes_per_launch')
+
+        def stage_ms(*names):
+            return sum(stages[k][0] for k in names) / args.steps
+
+        S_BYTES = 4 * h.C * h.NZ
+        dec_ms = stage_ms('crf_alpha', 'crf_backward', 'crf_viterbi')
+        inproj_ms = stage_ms('lstm_inproj_gemm')
+        head_ms = stage_ms('crf_head_gemm')
+        conv_ms = stage_ms('conv12_im2col', 'conv3_gemm')
+        per_stage = {
+            'lstm_inproj_gemm': {'bound': 'tensor', 'achieved': 5 * flops_per_span / (inproj_ms / 1e3) / 1e12,
+                                 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s'},
+            'crf_head_gemm': {'bound': 'hbm', 'achieved': (T * N * (h.C * h.NZ * 4 + FEATURES * 2)) / (head_ms / 1e3) / 1e9,
+                              'peak': pk['hbm_gbs'], 'unit': 'GB/s'},
+            'crf_decode': {'bound': 'hbm', 'achieved': (T * N * (2 * S_BYTES + 1)) / (dec_ms / 1e3) / 1e9,
+                           'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                           'note': 'algorithmic bytes (2*S+1) per (t, chunk), S = %d B of fp32 scores' % S_BYTES},
+            'conv_stem': {'bound': 'hbm', 'achieved': (N * (L * 4 + T * FEATURES * 2)) / (conv_ms / 1e3) / 1e9,
+                          'peak': pk['hbm_gbs'], 'unit': 'GB/s'},
+        }
+        for v in per_stage.values():
+            v['frac'] = v['achieved'] / v['peak']
         line = {
             'metric': 'signal samples/sec basecalled (sup@v3.3 XNA)', 'value': value, 'unit': 'samples/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: sup@v3.3 UB X (n_base 5), batch %d x %d-sample chunks per GPU, conv stem + '
-                                   '5 LSTM + CRF head + posteriors + Viterbi + left-pack; random-init weights; '
-                                   'per-step working set (activations 0.6 GB, scores 1.2 GB) exceeds the 126 MB L2, '
-                                   'no explicit flush' % (N, L),
-                       'batch_per_gpu': N, 'chunk': L, 'n_base': N_BASE, 'sharding': 'chunks across GPUs, no collective'},
+            'config': workload_config(N, L),
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': N * L * 4 * world,
                     'd2h_bytes_per_step': (N * T + N * 4) * world},
             'gpu_launches': launches,
             'roofline': {'bound': 'tensor', 'kernel': 'lstm_recurrence', 'achieved': achieved, 'peak': pk['tf_sustained'],
-                         'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': None,
+                         'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sustained'], 'traffic': traffic,
                          'peak_source': pk['source'] + ', sustained figure (kernel timed inside a long step)'},
+            'stage_rooflines': per_stage,
             'stages_ms_per_step': {k: v[0] / args.steps for k, v in stages.items()},
             'model_tflops': (sum(FLOP_PER_CHUNK.values()) * N * world) / (dev_ms / args.steps / 1e3) / 1e12,
             'clocks': clocks,
@@ -256,8 +287,8 @@ def main():
             cpu_reference_pass(4, cores)
             sec = cpu_reference_pass(n_chunks, cores, repeats=2)
             line['cpu_baseline'] = {'value': n_chunks * L / sec, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                                    'sample': '%d chunks x %d samples, best of 2 (torch fp32 encoder on all host '
-                                              'threads + C CRF decode on 1 thread)' % (n_chunks, L)}
+                                    'sample': '%d chunks x %d samples, best of 2 (torch fp32 encoder + C CRF decode, both on '
+                                              'all %d host threads)' % (n_chunks, L, cores)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -159,8 +159,9 @@ static void viterbi_forward(const lattice *L, const float *lp, size_t lp_stride,
 }
 
 /* decode_batch: labels (N,T) int8; optional post / lp outputs (T,N,C*NZ). */
-int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len, float *post, float *lp_out,
-                   int8_t *labels) {
+/* sequences [n_begin, n_end) only: lets the caller spread a batch over host threads (bench.py's CPU baseline) */
+int xbo_crf_decode_range(const float *scores, int T, int N, int n_begin, int n_end, int n_base, int state_len,
+                         float *post, float *lp_out, int8_t *labels) {
     lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
     size_t S = (size_t)L.C * L.NZ;
     float *alpha = (float *)malloc((size_t)(T + 1) * L.C * sizeof(float));
@@ -169,7 +170,7 @@ int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len,
     float *x = (float *)malloc(S * sizeof(float));
     float *sc = (float *)malloc(L.C * sizeof(float));
     if (!alpha || !bmax || !lp || !x || !sc) return -2;
-    for (int n = 0; n < N; n++) {
+    for (int n = n_begin; n < n_end; n++) {
         for (int c = 0; c < L.C; c++) alpha[c] = 0.0f;
         for (int t = 0; t < T; t++)
             alpha_step(&L, scores + ((size_t)t * N + n) * S, alpha + (size_t)t * L.C, alpha + (size_t)(t + 1) * L.C, 0);
@@ -209,6 +210,11 @@ int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len,
     }
     free(alpha); free(bmax); free(lp); free(x); free(sc);
     return 0;
+}
+
+int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len, float *post, float *lp_out,
+                   int8_t *labels) {
+    return xbo_crf_decode_range(scores, T, N, 0, N, n_base, state_len, post, lp_out, labels);
 }
 
 int xbo_crf_posteriors(const float *scores, int T, int N, int n_base, int state_len, float *post) {

@@ -92,6 +92,24 @@ def crf_decode(scores, n_base, state_len=3, want_post=False, want_lp=False):
     return out[0] if len(out) == 1 else tuple(out)
 
 
+def crf_decode_threads(scores, n_base, state_len=3, threads=1):
+    """crf_decode with the batch spread over `threads` host threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    s = _f32(scores)
+    T, N, _ = s.shape
+    labels = np.empty((N, T), dtype=np.int8)
+    threads = max(1, min(threads, N))
+    bounds = [(N * i // threads, N * (i + 1) // threads) for i in range(threads)]
+    fn = lib().xbo_crf_decode_range
+
+    def work(b):
+        return fn(_p(s), T, N, b[0], b[1], n_base, state_len, None, None, _p(labels))
+
+    with ThreadPoolExecutor(threads) as ex:
+        assert all(rc == 0 for rc in ex.map(work, bounds))
+    return labels
+
+
 def crf_viterbi(scores, n_base, state_len=3):
     s = _f32(scores)
     T, N, _ = s.shape
