@@ -1,6 +1,7 @@
 // C ABI of libxna_b200.so (include/xna_basecaller.h): handle life cycle, weight repacking, the encoder
 // pipeline (conv stem -> 5 LSTM layers -> CRF head), the CRF decode entry points and the host-buffer call.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "xb_common.cuh"
@@ -21,6 +22,7 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
+int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
 int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
                      const int32_t *lengths, int normalise, float *loss, cudaStream_t s);
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
@@ -335,6 +337,10 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
     // (a) input projection for all time steps: gates (T*N, 3072) = x W_ih^T + (b_ih + b_hh)
     {
         xb_stage_timer tm(h, XB_ST_INPROJ, s);
+        static const bool generic = getenv("XB_INPROJ_GENERIC") != nullptr;    // A/B switch: the generic tile kernel
+        if (!generic) {
+            if (int rc = xb_inproj_launch(h, x_tnc, lw.w_ih, lw.bias, h->gates, T * N, s)) return rc;
+        } else {
         CUtensorMap tmA, tmB;
         if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
         if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_ih, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
@@ -342,6 +348,7 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
         p.M = T * N; p.N = XB_GATES; p.K = XB_FEATURES;
         p.bias = lw.bias; p.out = h->gates; p.ldo = XB_GATES;
         if (int rc = xb_gemm_launch(h, EPI_INPROJ, tmA, tmB, p, s)) return rc;
+        }
     }
     // (b) recurrence: one fused GEMM + cell kernel per time step; direction by indexing
     xb_stage_timer tm(h, XB_ST_LSTM_REC, s);
