@@ -46,7 +46,7 @@ constexpr int D_COL = 384;                 // accumulators start after the 384 c
 constexpr int CTR_STRIDE = 32;             // ints between counters (one 128-byte line each)
 constexpr int MAX_CTRS = 64;
 
-template <int SUB, int NS> struct Cfg {
+template <int SUB, int NS, int EW> struct Cfg {          // EW = epilogue warps per sub-batch (4 or 8)
     static constexpr int NB = SUB * NS;                       // chunks per group
     static constexpr int H_BLOCK_BYTES = NS * 64 * 2;         // one K block: NS rows x 128 B
     static constexpr int H_PART_BYTES = KPB * H_BLOCK_BYTES;
@@ -54,11 +54,13 @@ template <int SUB, int NS> struct Cfg {
     static constexpr int G_BYTES = NS * 128 * 2;
     static constexpr int NBAR = HP + 1 + 4;                   // h_full[HP], d_full, g_full[2], g_empty[2]
     static constexpr int EPI_WARP0 = ((SUB + 1 + 3) / 4) * 4;
-    static constexpr int THREADS = (EPI_WARP0 + 4 * SUB) * 32;
-    static constexpr int STAGE_BYTES = NS * 16;               // per epilogue warp: [chunk][8 units] 16-bit
-    static constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + SUB * 4 * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    static constexpr int THREADS = (EPI_WARP0 + EW * SUB) * 32;
+    static constexpr int NC = NS * 4 / EW;                    // accumulator columns (chunks) per epilogue warp
+    static constexpr int STAGE_BYTES = NC * 16;               // per epilogue warp: [chunk][8 units] 16-bit
+    static constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + SUB * EW * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
     static_assert(D_COL + SUB * NS <= 512, "tensor memory columns");
     static_assert(NS % 16 == 0 && NS <= 32, "MMA N");
+    static_assert((EW == 4 || EW == 8) && NC % 16 == 0, "epilogue split");
     static_assert(SUB * NBAR * 8 + 16 <= 1024, "barrier block");
     static_assert(H_BLOCK_BYTES % 1024 == 0, "swizzle atom alignment");
 };
@@ -90,17 +92,17 @@ template <int NS> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, u
 template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
 template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
 
-template <bool BF16, int SUB, int NS>
-__global__ void __launch_bounds__(Cfg<SUB, NS>::THREADS, 1)
+template <bool BF16, int SUB, int NS, int EW>
+__global__ void __launch_bounds__(Cfg<SUB, NS, EW>::THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
     using X = xb16<BF16>;
-    using C = Cfg<SUB, NS>;
+    using C = Cfg<SUB, NS, EW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *hbuf = smem;                                       // [SUB][H_BYTES]
     uint8_t *gbuf = smem + SUB * C::H_BYTES;                    // [SUB][2][G_BYTES]
-    uint8_t *stage = gbuf + SUB * 2 * C::G_BYTES;               // [SUB][4][STAGE_BYTES]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + SUB * 4 * C::STAGE_BYTES);
+    uint8_t *stage = gbuf + SUB * 2 * C::G_BYTES;               // [SUB][EW][STAGE_BYTES]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + SUB * EW * C::STAGE_BYTES);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + SUB * C::NBAR);
     auto h_full = [&](int sub, int part) { return bars + sub * C::NBAR + part; };
     auto d_full = [&](int sub) { return bars + sub * C::NBAR + HP; };
@@ -125,7 +127,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             mbar_init(d_full(sub), 1);
             for (int q = 0; q < 2; q++) {
                 mbar_init(g_full(sub, q), 1);
-                mbar_init(g_empty(sub, q), 4);
+                mbar_init(g_empty(sub, q), EW);
             }
         }
         fence_barrier_init();
@@ -182,7 +184,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 }
                 if (s > 0) {
                     const int tp = p.reverse ? t + 1 : t - 1;
-                    const int need = TILES * 4 * s;          // every epilogue warp of the group has published step s-1
+                    const int need = TILES * EW * s;         // every epilogue warp of the group has published step s-1
                     DBG(sub, 0);
                     while (ld_acquire_gpu(ctr) < need) {
                     }
@@ -238,14 +240,16 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             }
         }
     } else if (warp >= C::EPI_WARP0) {
-        // ------------------------------------------------------------------ epilogue (4 warps per sub-batch)
-        constexpr int CELLS = NS / 4;
-        const int sub = (warp - C::EPI_WARP0) >> 2, q = warp & 3;
+        // ------------------------------------------------------------------ epilogue (EW warps per sub-batch: warp % 4 =
+        // TMEM lane quarter; with EW = 8 the second four take the upper half of the chunk columns)
+        constexpr int NC = C::NC, CELLS = NC / 4;
+        const int ew = (warp - C::EPI_WARP0) % EW, sub = (warp - C::EPI_WARP0) / EW, q = warp & 3;
+        const int col0 = (ew >> 2) * NC;                     // first chunk column of this warp
         const int gt = lane & 3, ul = lane >> 2;             // gate held after the TMEM load; unit within the warp
         const int unit = q * 8 + ul;                         // unit within the tile
         const int row0 = sub_row0(sub);
         const int cnt = b0 + ((sub + 1) * count) / SUB - row0;   // valid chunks of this sub-batch (<= NS)
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + D_COL + sub * NS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + D_COL + sub * NS + col0;
         int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
         const bool bit0 = lane & 1, bit1 = lane & 2;
         float cst[CELLS];
@@ -255,21 +259,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         for (int s = 0; s < T; s++) {
             const int t = p.reverse ? T - 1 - s : s;
             const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * 2 + (s & 1)) * C::G_BYTES);
-            uint32_t acc[NS];
+            uint32_t acc[NC];
             if (s > 0) {
                 mbar_wait(d_full(sub), (s - 1) & 1);
                 tc_fence_after();
-                if (q == 0 && lane == 0) DBG(sub, 9);
-                tmem_ld_cols<NS>(taddr, acc);
+                if (ew == 0 && lane == 0) DBG(sub, 9);
+                tmem_ld_cols<NC>(taddr, acc);
                 tmem_ld_wait();
                 tc_fence_before();
-                if (q == 0 && lane == 0) DBG(sub, 10);
+                if (ew == 0 && lane == 0) DBG(sub, 10);
             } else {
 #pragma unroll
-                for (int i = 0; i < NS; i++) acc[i] = 0u;
+                for (int i = 0; i < NC; i++) acc[i] = 0u;
             }
             mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
-            if (q == 0 && lane == 0) DBG(sub, 11);
+            if (ew == 0 && lane == 0) DBG(sub, 11);
             // phase A: 4x4 transposes across the four lanes of a unit (lane `gt` ends with (i,f,g,o) of chunk 4i+gt);
             // all blocks first so that the shuffles pipeline
             float pre[CELLS][4];
@@ -288,7 +292,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 float r0 = __shfl_xor_sync(0xffffffffu, bit1 ? a0 : a2, 2);
                 float r1 = __shfl_xor_sync(0xffffffffu, bit1 ? a1 : a3, 2);
                 if (bit1) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
-                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (4 * i + gt) * 128 + unit * 4);
+                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (col0 + 4 * i + gt) * 128 + unit * 4);
                 const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
                 pre[i][0] = a0 + g01.x; pre[i][1] = a1 + g01.y; pre[i][2] = a2 + g23.x; pre[i][3] = a3 + g23.y;
             }
@@ -325,7 +329,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             for (int i = 0; i < CELLS; i++) rr[i] = rcpf(1.f + ei[i]);
             // h slice of the warp (NS chunks x 8 units) through a 16 B-per-chunk staging row: one 16-byte global
             // store per chunk instead of eight 2-byte ones
-            uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * 4 + q) * C::STAGE_BYTES));
+            uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES));
 #pragma unroll
             for (int i = 0; i < CELLS; i++) {
                 const float hn = eo[i] * (1.f - ei[i]) * rr[i];
@@ -333,15 +337,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 st[(4 * i + gt) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
             }
             __syncwarp();
-            if (lane < NS && lane < cnt)
-                *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + lane) * XB_FEATURES + j * 32 + q * 8) =
+            if (lane < NC && col0 + lane < cnt)
+                *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
                     reinterpret_cast<const uint4 *>(st)[lane];
-            if (q == 0 && lane == 0) DBG(sub, 12);
+            if (ew == 0 && lane == 0) DBG(sub, 12);
             __syncwarp();
             if (lane == 0) {
                 red_release_gpu_add(ctr, 1);                  // publishes the warp's stores (cumulative over __syncwarp)
                 mbar_arrive(g_empty(sub, s & 1));
-                if (q == 0) DBG(sub, 13);
+                if (ew == 0) DBG(sub, 13);
             }
         }
     }
@@ -353,15 +357,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     }
 }
 
-template <bool BF16, int SUB, int NS>
+template <bool BF16, int SUB, int NS, int EW>
 int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
-    using C = Cfg<SUB, NS>;
+    using C = Cfg<SUB, NS, EW>;
     CUtensorMap tmY, tmG;
     if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
     if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
     const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
     const int block_cap = max_groups * C::NB;
-    auto fn = lstm_persistent_kernel<BF16, SUB, NS>;
+    auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW>;
     static bool configured = false;
     if (!configured) {
         XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -405,8 +409,8 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
     }
     static const int variant = getenv("XB_LSTM_VARIANT") ? atoi(getenv("XB_LSTM_VARIANT")) : 0;
     if (variant == 1)
-        return h->bf16 ? launch_cfg<true, 6, 16>(h, layer, y_tnc, T, N, reverse, s)
-                       : launch_cfg<false, 6, 16>(h, layer, y_tnc, T, N, reverse, s);
-    return h->bf16 ? launch_cfg<true, 3, 32>(h, layer, y_tnc, T, N, reverse, s)
-                   : launch_cfg<false, 3, 32>(h, layer, y_tnc, T, N, reverse, s);
+        return h->bf16 ? launch_cfg<true, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s)
+                       : launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
+    return h->bf16 ? launch_cfg<true, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s)
+                   : launch_cfg<false, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s);
 }
