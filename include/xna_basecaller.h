@@ -135,6 +135,14 @@ int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_firs
               const int32_t *chunk_count, const int32_t *read_len, int n_reads, int chunksize,
               int overlap, int stride, int8_t *out, int out_stride, int32_t *out_len, void *stream);
 
+/* util.chunk (util.py:152-166) for a whole read set resident on the device: signal holds the reads back to back
+ * (sig_dtype XB_SIG_F32 or XB_SIG_I16), read r occupies [read_offset[r], read_offset[r] + read_len[r]); chunk c is
+ * samples [chunk_start[c], chunk_start[c] + L) of read chunk_read[c], zero where that runs off the read (a negative
+ * start is the left padding of a short read).  out (n_chunks, L) fp32. */
+int xb_gather_chunks(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
+                     const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
+                     int L, float *out, void *stream);
+
 /* crf.basecall.compute_scores end to end with HOST buffers (crf/basecall.py:27-82): H2D of the
  * chunk batch, encoder, decode, D2H of the packed sequences; synchronises.  signal_host (N, L) fp32,
  * seq_host (N, T) int8, lens_host (N).  Pinned host memory makes the copies asynchronous. */

@@ -128,3 +128,31 @@ def test_ctc_crf_methods(model5, golden):
     want = bo.CRF(3, ALPHABETS[5]).reverse_complement(s.cpu())
     assert torch.equal(sd.reverse_complement(s).cpu(), want)
     np.testing.assert_allclose((sd.normalise(s)).cpu().numpy(), bo.CRF(3, ALPHABETS[5]).normalise(s.cpu()).numpy(), atol=1e-4)
+
+
+def test_read_set_pipeline_matches_basecall(model5):
+    """Device-side chunking + stitching of a whole read set gives exactly the strings of the reference-shaped
+    basecall() iterator (short, exact-multiple, stub and multi-chunk reads; ragged last batch)."""
+    from xna_basecaller_b200 import pipeline
+    from xna_basecaller_b200.crf import basecall
+
+    class Read:
+        def __init__(self, rid, sig):
+            self.read_id, self.signal = rid, sig
+
+    rs = np.random.RandomState(5)
+    lengths = [700, 1000, 1001, 2350, 1900, 3100, 999, 4600, 1, 2800]
+    sigs = [rs.randn(L).astype(np.float32) for L in lengths]
+    want = [res['sequence'] for _, res in basecall(model5, iter([Read(i, s) for i, s in enumerate(sigs)]),
+                                                   chunksize=1000, overlap=100, batchsize=4)]
+    got, counters = pipeline.ReadSetBasecaller(model5, chunksize=1000, overlap=100, batchsize=7).basecall(sigs)
+    assert got == want
+    assert counters['reads'] == len(sigs) and counters['samples'] == sum(lengths)
+    assert counters['chunks'] == sum(len(pipeline.plan_chunks([L], 1000, 100)['chunk_read']) for L in lengths)
+    # int16 signal takes the same route (values are exactly representable)
+    ints = [np.round(s * 50).astype(np.int16) for s in sigs[:4]]
+    a, _ = pipeline.ReadSetBasecaller(model5, 1000, 100, 5).basecall(ints)
+    b, _ = pipeline.ReadSetBasecaller(model5, 1000, 100, 5).basecall([x.astype(np.float32) for x in ints])
+    assert a == b
+    shard, table = pipeline.basecall_sharded(model5, sigs, 1000, 100, 7, rank=1, world=2)
+    assert shard == {i: want[i] for i in range(1, len(sigs), 2)} and table['reads'] == [5.0]

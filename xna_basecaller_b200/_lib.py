@@ -23,7 +23,7 @@ SYMBOLS = (
     'xb_load_lstm_weights', 'xb_load_head_weights', 'xb_conv_stem_fwd',
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
-    'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+    'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_gather_chunks', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
@@ -65,6 +65,7 @@ def load():
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
     lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
+    lib.xb_gather_chunks.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp]
     lib.xb_compute_scores_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.xb_launch_count.restype = ctypes.c_int64
     lib.xb_launch_count.argtypes = [vp]
@@ -314,6 +315,16 @@ class Handle:
         self._check(self.lib.xb_stitch(self.h, _ptr(rows), T, _ptr(cf), _ptr(cc), _ptr(rl), n_reads, chunksize, overlap,
                                        stride, _ptr(out), out_stride, _ptr(out_len), _stream(self.device)), 'xb_stitch')
         return out, out_len
+
+    def gather_chunks(self, signal, read_offset, read_len, chunk_read, chunk_start, L, out=None):
+        """chunk batch (n_chunks, L) fp32 cut on the device from a resident read set (fp32 or int16)."""
+        code = {torch.float32: XB_SIG_F32, torch.int16: XB_SIG_I16}[signal.dtype]
+        n = chunk_read.numel()
+        if out is None:
+            out = torch.empty(n, L, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_gather_chunks(self.h, _ptr(signal), code, _ptr(read_offset), _ptr(read_len), _ptr(chunk_read),
+                                              _ptr(chunk_start), n, L, _ptr(out), _stream(self.device)), 'xb_gather_chunks')
+        return out
 
     def compute_scores_host(self, signal_host, seq_host=None, lens_host=None):
         """signal_host: (N, L) fp32 CPU tensor (pinned for async copies) -> packed sequences on the host."""

@@ -48,6 +48,23 @@ __global__ void stitch_kernel(const int8_t *__restrict__ rows, int T, const int3
     if (lane == 0) out_len[r] = min(pos, out_stride);
 }
 
+// ---- chunk gather ------------------------------------------------------------------------------------
+// util.chunk (bonito/util.py:152-166) for a whole read set on the device: chunk c of the batch is samples
+// [start, start + L) of read chunk_read[c]; start < 0 means a short read, left-padded with zeros (:160).
+template <typename SIG>
+__global__ void gather_chunks_kernel(const SIG *__restrict__ signal, const int64_t *__restrict__ read_offset,
+                                     const int32_t *__restrict__ read_len, const int32_t *__restrict__ chunk_read,
+                                     const int32_t *__restrict__ chunk_start, int L, float *__restrict__ out) {
+    const int c = blockIdx.y;
+    const int r = chunk_read[c], start = chunk_start[c], len = read_len[r];
+    const SIG *src = signal + read_offset[r];
+    float *dst = out + (size_t)c * L;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+        const int p = start + i;
+        dst[i] = (p >= 0 && p < len) ? (float)src[p] : 0.0f;
+    }
+}
+
 // ---- CTC-CRF loss -----------------------------------------------------------------------------------
 __device__ __forceinline__ float logaddexp_exact(float a, float b) {
     float m = fmaxf(a, b);
@@ -115,6 +132,23 @@ int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk
     const int warps = 4;
     stitch_kernel<<<(n_reads + warps - 1) / warps, warps * 32, 0, s>>>(rows, T, chunk_first, chunk_count, read_len, n_reads,
                                                                        chunksize, overlap, stride, out, out_stride, out_len);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
+                          const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
+                          int L, float *out, cudaStream_t s) {
+    XB_REQUIRE(h, n_chunks > 0 && L > 0, "bad gather arguments");
+    dim3 grid((L + 1023) / 1024, n_chunks);
+    if (sig_dtype == XB_SIG_F32)
+        gather_chunks_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float *>(signal), read_offset, read_len,
+                                                         chunk_read, chunk_start, L, out);
+    else if (sig_dtype == XB_SIG_I16)
+        gather_chunks_kernel<int16_t><<<grid, 256, 0, s>>>(reinterpret_cast<const int16_t *>(signal), read_offset, read_len,
+                                                           chunk_read, chunk_start, L, out);
+    else
+        return xb_fail(h, XB_ERR_ARG, "gather supports fp32 and int16 signal");
     XB_LAUNCH_CHECK(h);
     return XB_OK;
 }

@@ -29,6 +29,10 @@ int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk
                    const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out,
                    int out_stride, int32_t *out_len, cudaStream_t s);
 
+int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
+                          const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
+                          int L, float *out, cudaStream_t s);
+
 namespace {
 
 int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
@@ -472,6 +476,14 @@ int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_firs
     XB_REQUIRE(h, rows && chunk_first && chunk_count && read_len && out && out_len, "NULL buffer");
     return xb_stitch_impl(h, rows, T, chunk_first, chunk_count, read_len, n_reads, chunksize, overlap, stride, out,
                           out_stride, out_len, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int xb_gather_chunks(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset, const int32_t *read_len,
+                     const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks, int L, float *out, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, signal && read_offset && read_len && chunk_read && chunk_start && out, "NULL buffer");
+    return xb_gather_chunks_impl(h, signal, sig_dtype, read_offset, read_len, chunk_read, chunk_start, n_chunks, L, out,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L, int8_t *seq_host, int32_t *lens_host,

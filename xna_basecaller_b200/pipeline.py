@@ -56,3 +56,66 @@ def gather_counters(counters, device=None):
         out = [mine]
     table = torch.stack(out).cpu().numpy()
     return {k: table[:, i].tolist() for i, k in enumerate(names)}
+
+
+class ReadSetBasecaller:
+    """Basecall a whole read set on one GPU without per-chunk host work (BASELINE config 4, one rank of it).
+
+    model: xna_basecaller_b200.crf.Model on a CUDA device.  basecall(signals) takes a list of 1-D float32 (or int16)
+    numpy arrays and returns (list of base strings in input order, counters).  Reads are uploaded once (pinned
+    staging, one H2D), chunk batches are cut on the device (xb_gather_chunks: the windows of util.chunk), every batch
+    runs the fused encoder + CRF decode into one (n_chunks, T) int8 row buffer, the rows are stitched on the device
+    (xb_stitch: util.stitch + to_str semantics) and only the stitched letters and lengths come back."""
+
+    def __init__(self, model, chunksize=4000, overlap=500, batchsize=512):
+        self.model, self.chunksize, self.overlap, self.batchsize = model, chunksize, overlap, batchsize
+        self.stride = model.stride
+        self.device = next(model.parameters()).device
+
+    def basecall(self, signals):
+        import time
+        dev, cs, ov, T = self.device, self.chunksize, self.overlap, self.chunksize // self.stride
+        n_reads = len(signals)
+        if n_reads == 0:
+            return [], {'reads': 0, 'samples': 0, 'chunks': 0, 'seconds': 0.0}
+        lengths = np.fromiter((len(s) for s in signals), dtype=np.int64, count=n_reads)
+        plan = plan_chunks(lengths, cs, ov)
+        n_chunks = len(plan['chunk_read'])
+        offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
+        dtype = torch.int16 if signals[0].dtype == np.int16 else torch.float32
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        host = torch.empty(int(lengths.sum()), dtype=dtype).pin_memory()
+        hv = host.numpy()
+        for o, s in zip(offsets, signals):
+            hv[o:o + len(s)] = s
+        sig = host.to(dev, non_blocking=True)
+        as_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+        read_offset, read_len = as_dev(offsets, torch.int64), as_dev(lengths, torch.int32)
+        chunk_read, chunk_start = as_dev(plan['chunk_read'], torch.int32), as_dev(plan['chunk_start'], torch.int32)
+
+        eng = self.model.seqdist.engine
+        h = eng.get(dev, min(self.batchsize, n_chunks), T, bf16=next(self.model.parameters()).dtype == torch.bfloat16)
+        self.model.encoder.sync_weights(h)
+        rows = torch.empty(n_chunks, T, dtype=torch.int8, device=dev)
+        batch = torch.empty(min(self.batchsize, n_chunks), cs, dtype=torch.float32, device=dev)
+        for lo in range(0, n_chunks, self.batchsize):
+            hi = min(lo + self.batchsize, n_chunks)
+            x = h.gather_chunks(sig, read_offset, read_len, chunk_read[lo:hi], chunk_start[lo:hi], cs, out=batch[:hi - lo])
+            scores = h.encoder(x)
+            seq, _, _ = h.decode(scores, want_qstring=False)
+            rows[lo:hi] = seq
+        out_stride = int(plan['chunk_count'].max()) * T
+        out, out_len = h.stitch(rows, plan['chunk_first'], plan['chunk_count'], lengths, cs, ov, self.stride, out_stride)
+        out_host, len_host = out.cpu().numpy(), out_len.cpu().numpy()
+        seconds = time.perf_counter() - t0
+        strings = [out_host[i, :len_host[i]].astype('u1').tobytes().decode('ascii') for i in range(n_reads)]
+        return strings, {'reads': n_reads, 'samples': int(lengths.sum()), 'chunks': n_chunks, 'seconds': seconds}
+
+
+def basecall_sharded(model, signals, chunksize=4000, overlap=500, batchsize=512, rank=0, world=1):
+    """One rank's share of a read set (reads r with r mod world == rank) + the gathered per-rank counters."""
+    mine = shard_reads(len(signals), rank, world)
+    strings, counters = ReadSetBasecaller(model, chunksize, overlap, batchsize).basecall([signals[i] for i in mine])
+    table = gather_counters(counters, device=next(model.parameters()).device if world > 1 else None)
+    return dict(zip(mine.tolist(), strings)), table
