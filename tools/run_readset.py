@@ -18,11 +18,17 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from oracle import bonito_oracle as bo                 # weight generator only
 from xna_basecaller_b200 import pipeline
 from xna_basecaller_b200.crf import Model
-from test_cpu_host import sup_config
+
+
+def sup_config(alphabet):
+    return {'global_norm': {'state_len': 3}, 'input': {'features': 1}, 'labels': {'labels': list(alphabet)},
+            'model': {'package': 'xna_basecaller_b200.crf'},
+            'encoder': {'stride': 5, 'activation': 'swish', 'features': 768, 'winlen': 19, 'scale': 5.0,
+                        'rnn_type': 'lstm', 'blank_score': 2.0}}
+
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
