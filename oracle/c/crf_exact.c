@@ -258,3 +258,5 @@ int xbo_pack(const int8_t *labels, int N, int T, const char *alphabet, int8_t *s
 
 void xbo_expf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_expf(x[i]); }
 void xbo_logf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_logf(x[i]); }
+void xbo_expf_le0_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_expf_le0(x[i]); }
+void xbo_logf_norm_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_logf_norm(x[i]); }

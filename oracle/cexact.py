@@ -57,6 +57,21 @@ def logf(x):
     return y
 
 
+def _apply(name, x):
+    x = _f32(x)
+    y = np.empty_like(x)
+    getattr(lib(), name)(_p(x), _p(y), ctypes.c_long(x.size))
+    return y
+
+
+def expf_le0(x):
+    return _apply('xbo_expf_le0_array', x)
+
+
+def logf_norm(x):
+    return _apply('xbo_logf_norm_array', x)
+
+
 def crf_alpha(scores, n_base, state_len=3):
     s = _f32(scores)
     T, N, _ = s.shape

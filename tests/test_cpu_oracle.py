@@ -31,6 +31,15 @@ def test_exact_expf_logf_within_2ulp():
     assert cexact.logf(np.float32([1.0]))[0] == 0.0
 
 
+def test_exact_math_fast_variants():
+    """The branch-trimmed exp / log the CUDA sweeps use return the same bits as the general ones on their domain."""
+    rs = np.random.RandomState(1)
+    x = np.concatenate([-np.abs(rs.uniform(0, 100, 200000)), -rs.exponential(3.0, 200000), [0.0, -0.0, -86.0, -86.5, -1e38, -np.inf]]).astype(np.float32)
+    assert np.array_equal(cexact.expf_le0(x).view(np.uint32), cexact.expf(x).view(np.uint32))
+    y = np.concatenate([np.exp(rs.uniform(-18.5, 10, 400000)), [1e-8, 1.0, 750.0, 1.00000001e-8]]).astype(np.float32)
+    assert np.array_equal(cexact.logf_norm(y).view(np.uint32), cexact.logf(y).view(np.uint32))
+
+
 # ----------------------------------------------------------------------------- CRF vs golden / brute force
 @pytest.mark.parametrize('n_base', [4, 5, 6])
 @pytest.mark.parametrize('seed', [0, 1])

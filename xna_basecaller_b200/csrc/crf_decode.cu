@@ -61,10 +61,10 @@ template <int NZ> __device__ __forceinline__ float lse_exact(const float (&x)[NZ
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < NZ; k++) {
-        float e = xb_expf(XB_SUB(x[k], m));
+        float e = xb_expf_le0(XB_SUB(x[k], m));
         s = (k == 0) ? e : XB_ADD(s, e);
     }
-    return XB_ADD(m, xb_logf(s));
+    return XB_ADD(m, xb_logf_norm(s));
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -281,7 +281,7 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
         if (act) {
 #pragma unroll
             for (int k = 0; k < NZ; k++) {
-                x[k] = xb_expf(XB_SUB(x[k], gmax));
+                x[k] = xb_expf_le0(XB_SUB(x[k], gmax));
                 s = (k == 0) ? x[k] : XB_ADD(s, x[k]);
             }
         }
@@ -297,7 +297,7 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
             for (int k = 0; k < NZ; k++) {
                 float p = XB_MUL(x[k], inv);
                 if (post_out) post_out[((size_t)t * N + n) * S + c * NZ + k] = p;
-                LP[c * NZ + k] = xb_logf(XB_ADD(p, XB_POST_EPS));
+                LP[c * NZ + k] = xb_logf_norm(XB_ADD(p, XB_POST_EPS));
             }
         }
         __syncthreads();                                                        // B3

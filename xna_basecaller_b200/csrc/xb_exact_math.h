@@ -103,4 +103,51 @@ XB_HD float xb_logf(float x) {
     return XB_FMA(fe, 0.693359375f, r);
 }
 
+// Specialisations for the arguments the decode sweeps actually produce; same bits as the general functions on
+// their domain (tests/test_cpu_oracle.py::test_exact_math_fast_variants), fewer instructions:
+//   xb_expf_le0: x <= 0 (a score minus a running maximum), so no overflow branch;
+//   xb_logf_norm: x a positive normal number (a sum of exponentials >= 1, or a posterior + 1e-8).
+XB_HD float xb_expf_le0(float x) {
+    if (!(x >= -86.0f)) return 0.0f;
+    const float magic = 12582912.0f;
+    float t = XB_FMA(x, 1.44269504088896341f, magic);
+    float n = XB_SUB(t, magic);
+    float r = XB_FMA(n, -0.693359375f, x);
+    r = XB_FMA(n, 2.12194440e-4f, r);
+    float z = XB_MUL(r, r);
+    float p = 1.9875691500e-4f;
+    p = XB_FMA(p, r, 1.3981999507e-3f);
+    p = XB_FMA(p, r, 8.3334519073e-3f);
+    p = XB_FMA(p, r, 4.1665795894e-2f);
+    p = XB_FMA(p, r, 1.6666665459e-1f);
+    p = XB_FMA(p, r, 5.0000001201e-1f);
+    p = XB_FMA(p, z, r);
+    p = XB_ADD(p, 1.0f);
+    int32_t ni = (int32_t)n;
+    return XB_U2F(XB_F2U(p) + ((uint32_t)ni << 23));
+}
+
+XB_HD float xb_logf_norm(float x) {
+    uint32_t iy = XB_F2U(x) - 0x3f3504f3u;
+    int32_t e = (int32_t)iy >> 23;
+    float m = XB_U2F((iy & 0x007fffffu) + 0x3f3504f3u);
+    float f = XB_SUB(m, 1.0f);
+    float z = XB_MUL(f, f);
+    float p = 7.0376836292e-2f;
+    p = XB_FMA(p, f, -1.1514610310e-1f);
+    p = XB_FMA(p, f, 1.1676998740e-1f);
+    p = XB_FMA(p, f, -1.2420140846e-1f);
+    p = XB_FMA(p, f, 1.4249322787e-1f);
+    p = XB_FMA(p, f, -1.6668057665e-1f);
+    p = XB_FMA(p, f, 2.0000714765e-1f);
+    p = XB_FMA(p, f, -2.4999993993e-1f);
+    p = XB_FMA(p, f, 3.3333331174e-1f);
+    p = XB_MUL(XB_MUL(p, f), z);
+    float fe = (float)e;
+    p = XB_FMA(fe, -2.12194440e-4f, p);
+    p = XB_FMA(z, -0.5f, p);
+    float r = XB_ADD(f, p);
+    return XB_FMA(fe, 0.693359375f, r);
+}
+
 #endif  // XB_EXACT_MATH_H
