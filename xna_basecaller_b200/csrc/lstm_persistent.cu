@@ -186,7 +186,10 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     const int tp = p.reverse ? t + 1 : t - 1;
                     const int need = TILES * EW * s;         // every epilogue warp of the group has published step s-1
                     DBG(sub, 0);
-                    while (ld_acquire_gpu(ctr) < need) {
+                    // relaxed poll (an acquire load costs a CCTL.IVALL per iteration and ~600 cycles per hand-off):
+                    // the producers' release made h visible in L2 before the counter moved, and the only reader of
+                    // that data is the TMA unit, which is issued after (control dependence) and reads L2 directly
+                    while (ld_relaxed_gpu(ctr) < need) {
                     }
                     DBG(sub, 1);
                     fence_proxy_async_global();
