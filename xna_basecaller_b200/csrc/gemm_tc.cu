@@ -355,10 +355,10 @@ template <bool BF16, int EPI>
 static int launch_one(xb_handle *h, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int rows_a,
                       cudaStream_t s) {
     auto k = gemm_tc_kernel<BF16, EPI>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static bool configured[64] = {};   // per instantiation and device (function attributes live in the context)
+    if (!configured[h->device & 63]) {
         XB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
+        configured[h->device & 63] = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (rows_a + BM - 1) / BM);
     k<<<grid, 256, SMEM_BYTES, s>>>(tmA, tmB, p);

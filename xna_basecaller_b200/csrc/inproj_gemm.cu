@@ -238,17 +238,18 @@ int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float 
     p.M = M;
     const int ntiles = (M + BM - 1) / BM;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
-    static bool configured[2] = {false, false};
+    static bool configured[2][64] = {};   // per device: function attributes live in the device's context
+    const int dv = h->device & 63;
     if (h->bf16) {
-        if (!configured[1]) {
+        if (!configured[1][dv]) {
             XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[1] = true;
+            configured[1][dv] = true;
         }
         inproj_kernel<true><<<grid, 256, SMEM_BYTES, s>>>(tmW, p);
     } else {
-        if (!configured[0]) {
+        if (!configured[0][dv]) {
             XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[0] = true;
+            configured[0][dv] = true;
         }
         inproj_kernel<false><<<grid, 256, SMEM_BYTES, s>>>(tmW, p);
     }

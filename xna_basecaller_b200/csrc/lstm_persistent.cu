@@ -369,10 +369,10 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
     const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
     const int block_cap = max_groups * C::NB;
     auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};      // per device: function attributes live in the device's context
+    if (!configured[h->device & 63]) {
         XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
+        configured[h->device & 63] = true;
     }
     for (int batch0 = 0; batch0 < N; batch0 += block_cap) {
         PLParams p;

@@ -99,6 +99,7 @@ int repack(xb_handle *h, const float *src, void *dst, int rows_dst, int cols_dst
 }
 
 int check_tn(xb_handle *h, int T, int N) {
+    XB_CUDA(h, cudaSetDevice(h->device));      // every compute entry point passes here: kernels go to the handle's device
     XB_REQUIRE(h, T > 0 && N > 0, "T and N must be positive (got T=%d N=%d)", T, N);
     XB_REQUIRE(h, T <= h->max_T && N <= h->max_N, "T=%d N=%d exceed the handle capacity max_T=%d max_N=%d", T, N, h->max_T,
                h->max_N);
@@ -474,6 +475,7 @@ int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_firs
               int32_t *out_len, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
     XB_REQUIRE(h, rows && chunk_first && chunk_count && read_len && out && out_len, "NULL buffer");
+    XB_CUDA(h, cudaSetDevice(h->device));
     return xb_stitch_impl(h, rows, T, chunk_first, chunk_count, read_len, n_reads, chunksize, overlap, stride, out,
                           out_stride, out_len, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -482,6 +484,7 @@ int xb_gather_chunks(xb_handle *h, const void *signal, int sig_dtype, const int6
                      const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks, int L, float *out, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
     XB_REQUIRE(h, signal && read_offset && read_len && chunk_read && chunk_start && out, "NULL buffer");
+    XB_CUDA(h, cudaSetDevice(h->device));
     return xb_gather_chunks_impl(h, signal, sig_dtype, read_offset, read_len, chunk_read, chunk_start, n_chunks, L, out,
                                  reinterpret_cast<cudaStream_t>(stream));
 }
