@@ -125,6 +125,10 @@ def test_ctc_crf_methods(model5, golden):
     loss = sd.ctc_loss(s, tg.cuda(), tl.cuda(), reduction='none')
     np.testing.assert_allclose(loss.cpu().numpy(), g['n5_s0_ctc_loss'], rtol=1e-5)
     assert abs(sd.ctc_loss(s, tg.cuda(), tl.cuda()).item() - g['n5_s0_ctc_loss'].mean()) < 1e-4
+    tp, ip = sd.compute_transition_probs(s, sd.backward_scores(s))
+    ref = bo.CRF(3, ALPHABETS[5])
+    tp_ref, ip_ref = ref.compute_transition_probs(s.cpu(), ref.backward_scores(s.cpu()))
+    assert (tp.cpu() - tp_ref).abs().max().item() < 1e-5 and (ip.cpu() - ip_ref).abs().max().item() < 1e-5
     want = bo.CRF(3, ALPHABETS[5]).reverse_complement(s.cpu())
     assert torch.equal(sd.reverse_complement(s).cpu(), want)
     np.testing.assert_allclose((sd.normalise(s)).cpu().numpy(), bo.CRF(3, ALPHABETS[5]).normalise(s.cpu()).numpy(), atol=1e-4)

@@ -106,6 +106,15 @@ class CTC_CRF:
             return loss
         raise ValueError('Unknown reduction type {}'.format(reduction))
 
+    def compute_transition_probs(self, scores, betas):
+        """Per-state transition probabilities in (old_state, emitted_base) layout and initial state probabilities
+        (crf/model.py:63-76; only the reference's unused duplex CLI consumes them).  betas come from the CUDA backward
+        scan (backward_scores); the re-layout and the two small softmaxes are torch ops on the same device."""
+        T, N, _ = scores.shape
+        lt = scores.reshape(T, N, -1, self.n_base + 1) + betas[1:, :, :, None]
+        lt = torch.cat([lt[:, :, :, [0]], lt[:, :, :, 1:].transpose(3, 2).reshape(T, N, -1, self.n_base)], dim=-1)
+        return torch.softmax(lt, dim=-1), torch.softmax(betas[0], dim=-1)
+
     # Index permutations of the score tensor (no arithmetic): device-side tensor views, as in the reference.
     def reverse_complement(self, scores):
         T, N, _ = scores.shape
