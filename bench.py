@@ -64,6 +64,25 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        try:                                            # NVML: a sample every 20 ms (nvidia-smi needs ~50 ms per call)
+            import pynvml
+            pynvml.nvmlInit()
+            dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM)
+            bits = {'hw_slowdown': pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(dev)
+                watts = pynvml.nvmlDeviceGetPowerUsage(dev) / 1000.0
+                self.rows.append([str(sm), str(mx), str(watts)] + ['Active' if reasons & bits[n] else 'Not Active' for n in names])
+                self.stop_flag.wait(0.02)
+            return
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
@@ -71,7 +90,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(',')])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -151,7 +170,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'])
