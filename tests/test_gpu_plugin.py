@@ -128,7 +128,7 @@ def test_ctc_crf_methods(model5, golden):
     tp, ip = sd.compute_transition_probs(s, sd.backward_scores(s))
     ref = bo.CRF(3, ALPHABETS[5])
     tp_ref, ip_ref = ref.compute_transition_probs(s.cpu(), ref.backward_scores(s.cpu()))
-    assert (tp.cpu() - tp_ref).abs().max().item() < 1e-5 and (ip.cpu() - ip_ref).abs().max().item() < 1e-5
+    assert (tp.cpu() - tp_ref).abs().max().item() < 2e-4 and (ip.cpu() - ip_ref).abs().max().item() < 2e-4   # betas ~1e3: fp32 ulp 6e-5
     want = bo.CRF(3, ALPHABETS[5]).reverse_complement(s.cpu())
     assert torch.equal(sd.reverse_complement(s).cpu(), want)
     np.testing.assert_allclose((sd.normalise(s)).cpu().numpy(), bo.CRF(3, ALPHABETS[5]).normalise(s.cpu()).numpy(), atol=1e-4)
@@ -160,3 +160,32 @@ def test_read_set_pipeline_matches_basecall(model5):
     assert a == b
     shard, table = pipeline.basecall_sharded(model5, sigs, 1000, 100, 7, rank=1, world=2)
     assert shard == {i: want[i] for i in range(1, len(sigs), 2)} and table['reads'] == [5.0]
+
+
+def test_compute_scores_reverse_and_device_batches(model5):
+    """reverse=True permutes the score tensor (CTC_CRF.reverse_complement) between encoder and decode; a batch that
+    already lives on the device takes the same two-call route.  Both must equal the oracle's decode of the same scores."""
+    from xna_basecaller_b200.crf.basecall import compute_scores
+    x = synthetic_signal(33, 3, 500)
+    crf = bo.CRF(3, ALPHABETS[5])
+    with torch.no_grad():
+        scores = model5(x.cuda()).cpu()
+    for reverse in (False, True):
+        s = crf.reverse_complement(scores) if reverse else scores
+        want = bo.left_pack(crf.decode_batch(s), s.shape[0])
+        got = compute_scores(model5, x.cuda() if not reverse else x, reverse=reverse)
+        assert np.array_equal(got['sequence'].numpy(), want['sequence'])
+        assert np.array_equal(got['qstring'].numpy(), want['qstring'])
+
+
+def test_read_set_pipeline_edge_cases(model5):
+    from xna_basecaller_b200 import pipeline
+    caller = pipeline.ReadSetBasecaller(model5, chunksize=1000, overlap=100, batchsize=3)
+    assert caller.basecall([]) == ([], {'reads': 0, 'samples': 0, 'chunks': 0, 'seconds': 0.0})
+    one, c = caller.basecall([np.zeros(5, dtype=np.float32)])            # a single very short read: one padded chunk
+    assert len(one) == 1 and c['chunks'] == 1
+    rs = np.random.RandomState(9)
+    sig = rs.randn(1000).astype(np.float32)                               # exactly one chunk: stitch is the identity
+    (a,), _ = caller.basecall([sig])
+    (b,), _ = pipeline.ReadSetBasecaller(model5, 1000, 100, 64).basecall([sig])
+    assert a == b and len(a) > 0

@@ -17,6 +17,14 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) { uint32_t
 __device__ __forceinline__ void st_relaxed_v4(uint4 *p, uint4 v) { asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p) { uint4 v; asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v; }
 
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// mode 3: payload by a 256-byte bulk async store (smem -> global), wait_group, then a RELAXED flag; reader polls the
+// flag relaxed and checks the payload with relaxed loads (counts stale reads)
 // mode 0: relaxed flag ping-pong; 1: payload (plain st) + st.release flag / ld.acquire; 2: tagged 16-byte payload, relaxed
 __global__ void pingpong(uint32_t *flags, uint4 *payload, long long *out, int iters, int mode, int peer) {
     if (threadIdx.x != 0) return;
@@ -24,16 +32,33 @@ __global__ void pingpong(uint32_t *flags, uint4 *payload, long long *out, int it
     if (me < 0) return;
     uint32_t *mine = flags + me * 64, *other = flags + (1 - me) * 64;
     uint4 *pm = payload + me * 64, *po = payload + (1 - me) * 64;
+    __shared__ __align__(128) uint4 sbuf[16];
     long long t0 = clock64();
     for (int i = 1; i <= iters; i++) {
         if (me == 0) {
             if (mode == 0) { st_relaxed_u32(mine, i); while (ld_relaxed_u32(other) != (uint32_t)i) {} }
             else if (mode == 1) { pm[1] = make_uint4(i, i, i, i); st_release_u32(mine, i); while (ld_acquire_u32(other) != (uint32_t)i) {} if (ld_relaxed_v4(po + 1).x != (uint32_t)i) out[7]++; }
-            else { st_relaxed_v4(pm, make_uint4(i, 1, 2, 3)); while (ld_relaxed_v4(po).x != (uint32_t)i) {} }
+            else if (mode == 2) { st_relaxed_v4(pm, make_uint4(i, 1, 2, 3)); while (ld_relaxed_v4(po).x != (uint32_t)i) {} }
+            else {
+                for (int k = 0; k < 16; k++) sbuf[k] = make_uint4(i, k, i, k);
+                fence_proxy_async();
+                bulk_store(pm + 16, sbuf, 256);
+                st_relaxed_u32(mine, i);
+                while (ld_relaxed_u32(other) != (uint32_t)i) {}
+                if (ld_relaxed_v4(po + 16).x != (uint32_t)i || ld_relaxed_v4(po + 31).z != (uint32_t)i) out[7]++;
+            }
         } else {
             if (mode == 0) { while (ld_relaxed_u32(other) != (uint32_t)i) {} st_relaxed_u32(mine, i); }
             else if (mode == 1) { while (ld_acquire_u32(other) != (uint32_t)i) {} if (ld_relaxed_v4(po + 1).x != (uint32_t)i) out[7]++; pm[1] = make_uint4(i, i, i, i); st_release_u32(mine, i); }
-            else { while (ld_relaxed_v4(po).x != (uint32_t)i) {} st_relaxed_v4(pm, make_uint4(i, 1, 2, 3)); }
+            else if (mode == 2) { while (ld_relaxed_v4(po).x != (uint32_t)i) {} st_relaxed_v4(pm, make_uint4(i, 1, 2, 3)); }
+            else {
+                while (ld_relaxed_u32(other) != (uint32_t)i) {}
+                if (ld_relaxed_v4(po + 16).x != (uint32_t)i || ld_relaxed_v4(po + 31).z != (uint32_t)i) out[7]++;
+                for (int k = 0; k < 16; k++) sbuf[k] = make_uint4(i, k, i, k);
+                fence_proxy_async();
+                bulk_store(pm + 16, sbuf, 256);
+                st_relaxed_u32(mine, i);
+            }
         }
     }
     long long t1 = clock64();
@@ -62,7 +87,7 @@ int main(int argc, char **argv) {
     long long h[32];
     for (int peer : {1, 2, 37, 74, 111, 147}) {
         cudaMemset(out, 0, 256);
-        for (int mode = 0; mode < 3; mode++) {
+        for (int mode = 0; mode < 4; mode++) {
             cudaMemset(flags, 0, 4096); cudaMemset(payload, 0, 8192);
             int iters = 2000;
             void *args[] = {&flags, &payload, &out, &iters, &mode, &peer};
@@ -71,8 +96,8 @@ int main(int argc, char **argv) {
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         }
         cudaMemcpy(h, out, 256, cudaMemcpyDeviceToHost);
-        printf("peer CTA %3d: one-way hand-off  relaxed flag %5lld cyc | payload + release/acquire %5lld cyc | tagged 16 B relaxed %5lld cyc (stale payload reads: %lld)\n",
-               peer, h[0], h[1], h[2], h[7]);
+        printf("peer CTA %3d: one-way hand-off  relaxed flag %5lld cyc | payload + release/acquire %5lld cyc | tagged 16 B relaxed %5lld cyc | bulk store + wait_group + relaxed flag %5lld cyc (stale payload reads: %lld)\n",
+               peer, h[0], h[1], h[2], h[3], h[7]);
     }
     for (int grid : {1, 148}) {
         cudaMemset(out, 0, 256);
