@@ -30,7 +30,7 @@ constexpr int KB = XB_FEATURES / BK;                 // 12 K blocks
 constexpr int NT = XB_GATES / BNI;                   // 48 N tiles
 constexpr int KPS = 4;                               // K blocks per pipeline stage (one 3-D TMA box, 16 MMAs per wait)
 constexpr int SPT = KB / KPS;                        // stages per N tile
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int KBLOCK_BYTES = BNI * BK * 2;           // 8 KB: one [64 rows x 128 B] swizzle atom column
 constexpr int STAGE_BYTES = KPS * KBLOCK_BYTES;      // 32 KB
 constexpr int A_COLS = XB_FEATURES / 2;              // 384 TMEM columns hold the x block
