@@ -44,7 +44,7 @@ mine = pipeline.shard_reads(n_reads, rank, world)
 g = np.random.RandomState(1000 + rank)
 signals = [g.standard_normal(int(lengths[i])).astype(np.float32) for i in mine]
 caller = pipeline.ReadSetBasecaller(model, 4000, 500, 512)
-caller.basecall(signals[:64])                           # warm-up (handle creation, weight repack)
+caller.basecall(signals)                                # warm-up (handle, weights, pinned staging buffers)
 strings, counters = caller.basecall(signals)
 table = pipeline.gather_counters(counters, device=torch.device('cuda', local) if world > 1 else None)
 if rank == 0:
@@ -53,6 +53,7 @@ if rank == 0:
     print(json.dumps({'config': 'configs[3] scaled: %d reads, cs 4000, ov 500, batch 512, sharded r mod G' % n_reads,
                       'n_gpus': world, 'samples': total, 'seconds_max_rank': sec, 'samples_per_s': total / sec,
                       'chunks': sum(table['chunks']), 'reads_per_rank': table['reads'],
+                      'rank0_seconds': {k: v[0] for k, v in table.items() if k.startswith('seconds_')},
                       'mean_bases_per_read': float(np.mean([len(s) for s in strings]))}))
 if world > 1:
     dist.destroy_process_group()

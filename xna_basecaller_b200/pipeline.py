@@ -27,20 +27,22 @@ def plan_chunks(read_lengths, chunksize, overlap):
     Returns dict of int64 arrays: chunk_read (owning read), chunk_start (first sample within the read; negative
     for a short read = number of left-pad zeros), chunk_first / chunk_count (per read: its rows in the table).
     Windows are exactly those of util.chunk (bonito/util.py:152-166)."""
-    chunk_read, chunk_start, first, count = [], [], [], []
-    for r, n in enumerate(read_lengths):
-        n = int(n)
-        first.append(len(chunk_read))
-        if n < chunksize:
-            starts = [n - chunksize]                    # left pad with zeros (util.py:160)
-        else:
-            starts = chunk_starts(n, chunksize, overlap)
-        chunk_read += [r] * len(starts)
-        chunk_start += starts
-        count.append(len(starts))
-    as64 = lambda v: np.asarray(v, dtype=np.int64)
-    return {'chunk_read': as64(chunk_read), 'chunk_start': as64(chunk_start), 'chunk_first': as64(first),
-            'chunk_count': as64(count)}
+    n = np.asarray(read_lengths, dtype=np.int64)
+    step = chunksize - overlap
+    short = n < chunksize
+    stub = np.where(short, 0, (n - overlap) % step)
+    regular = np.where(short, 0, (n - stub - chunksize) // step + 1)      # windows of signal[stub:].unfold(...)
+    count = np.where(short, 1, regular + (stub > 0))
+    first = np.concatenate([[0], np.cumsum(count)[:-1]])
+    total = int(count.sum())
+    chunk_read = np.repeat(np.arange(len(n), dtype=np.int64), count)
+    k = np.arange(total, dtype=np.int64) - first[chunk_read]              # index of the chunk within its read
+    has_stub = (stub > 0)[chunk_read]
+    start = stub[chunk_read] + (k - has_stub) * step                      # k-th regular window (after the stub chunk)
+    start = np.where(has_stub & (k == 0), 0, start)                       # leading stub chunk = signal[:chunksize]
+    start = np.where(short[chunk_read], n[chunk_read] - chunksize, start) # short read: left pad (negative start)
+    return {'chunk_read': chunk_read, 'chunk_start': start.astype(np.int64), 'chunk_first': first.astype(np.int64),
+            'chunk_count': count.astype(np.int64)}
 
 
 def gather_counters(counters, device=None):
@@ -71,13 +73,22 @@ class ReadSetBasecaller:
         self.model, self.chunksize, self.overlap, self.batchsize = model, chunksize, overlap, batchsize
         self.stride = model.stride
         self.device = next(model.parameters()).device
+        self._pinned = {}                               # grow-only pinned staging buffers, reused across calls
+
+    def _staging(self, n, dtype):
+        buf = self._pinned.get(dtype)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            self._pinned[dtype] = buf
+        return buf[:n]
 
     def basecall(self, signals):
         import time
         dev, cs, ov, T = self.device, self.chunksize, self.overlap, self.chunksize // self.stride
         n_reads = len(signals)
         if n_reads == 0:
-            return [], {'reads': 0, 'samples': 0, 'chunks': 0, 'seconds': 0.0}
+            return [], {'reads': 0, 'samples': 0, 'chunks': 0, 'seconds': 0.0, 'seconds_stage_h2d': 0.0,
+                        'seconds_gpu_batches': 0.0, 'seconds_stitch_d2h': 0.0, 'seconds_strings': 0.0}
         lengths = np.fromiter((len(s) for s in signals), dtype=np.int64, count=n_reads)
         plan = plan_chunks(lengths, cs, ov)
         n_chunks = len(plan['chunk_read'])
@@ -85,15 +96,14 @@ class ReadSetBasecaller:
         dtype = torch.int16 if signals[0].dtype == np.int16 else torch.float32
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        host = torch.empty(int(lengths.sum()), dtype=dtype).pin_memory()
-        hv = host.numpy()
-        for o, s in zip(offsets, signals):
-            hv[o:o + len(s)] = s
+        host = self._staging(int(lengths.sum()), dtype)
+        np.concatenate(signals, out=host.numpy())          # one pass into pinned memory, then a single H2D
         sig = host.to(dev, non_blocking=True)
         as_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
         read_offset, read_len = as_dev(offsets, torch.int64), as_dev(lengths, torch.int32)
         chunk_read, chunk_start = as_dev(plan['chunk_read'], torch.int32), as_dev(plan['chunk_start'], torch.int32)
 
+        t1 = time.perf_counter()
         eng = self.model.seqdist.engine
         h = eng.get(dev, min(self.batchsize, n_chunks), T, bf16=next(self.model.parameters()).dtype == torch.bfloat16)
         self.model.encoder.sync_weights(h)
@@ -105,12 +115,17 @@ class ReadSetBasecaller:
             scores = h.encoder(x)
             seq, _, _ = h.decode(scores, want_qstring=False)
             rows[lo:hi] = seq
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
         out_stride = int(plan['chunk_count'].max()) * T
         out, out_len = h.stitch(rows, plan['chunk_first'], plan['chunk_count'], lengths, cs, ov, self.stride, out_stride)
         out_host, len_host = out.cpu().numpy(), out_len.cpu().numpy()
         seconds = time.perf_counter() - t0
-        strings = [out_host[i, :len_host[i]].astype('u1').tobytes().decode('ascii') for i in range(n_reads)]
-        return strings, {'reads': n_reads, 'samples': int(lengths.sum()), 'chunks': n_chunks, 'seconds': seconds}
+        flat = out_host.view('u1')
+        strings = [flat[i, :len_host[i]].tobytes().decode('ascii') for i in range(n_reads)]
+        return strings, {'reads': n_reads, 'samples': int(lengths.sum()), 'chunks': n_chunks, 'seconds': seconds,
+                         'seconds_stage_h2d': t1 - t0, 'seconds_gpu_batches': t2 - t1, 'seconds_stitch_d2h': seconds - (t2 - t0),
+                         'seconds_strings': time.perf_counter() - t0 - seconds}
 
 
 def basecall_sharded(model, signals, chunksize=4000, overlap=500, batchsize=512, rank=0, world=1):
