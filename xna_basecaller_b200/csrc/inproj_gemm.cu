@@ -17,6 +17,8 @@
 //
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 load the
 // x block into TMEM (thread = row) and run the epilogues (warp % 4 = TMEM lane quarter).
+#include <stdlib.h>
+
 #include "xb_common.cuh"
 #include "xb_ptx.cuh"
 #include "xb_gemm.cuh"
@@ -43,6 +45,8 @@ struct IPParams {
     const float *bias;        // (3072) fp32, same column order as the rows of W_ih
     uint16_t *out;            // (M, 3072) 16-bit
     int M;
+    int no_prefetch;
+    long long *dbg;           // optional (XB_INPROJ_DEBUG): stall cycles of the MMA thread of CTA 0: [acc_empty, full, issue, a_ready]
 };
 
 template <bool BF16>
@@ -103,18 +107,27 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, BM, BNI);
         uint32_t it = 0, nit = 0, tit = 0;
+        long long st_acc = 0, st_full = 0, st_issue = 0, st_a = 0, tt;
+        const bool dbg = p.dbg && blockIdx.x == 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tit++) {
+            tt = clock64();
             mbar_wait(a_ready, tit & 1);                       // x block of this tile is in tensor memory
             tc_fence_after();
+            st_a += clock64() - tt;
             for (int nt = 0; nt < NT; nt++, nit++) {
                 const int buf = nit & 1;
+                tt = clock64();
                 mbar_wait(&acc_empty[buf], ((nit >> 1) & 1) ^ 1);
                 tc_fence_after();
+                st_acc += clock64() - tt;
                 const uint32_t d = tmem_base + A_COLS + buf * BNI;
                 for (int ks = 0; ks < SPT; ks++, it++) {
                     const int s = it % STAGES;
+                    tt = clock64();
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
+                    st_full += clock64() - tt;
+                    tt = clock64();
                     if (elect_one()) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
                         const uint32_t a0 = tmem_base + ks * KPS * (BK / 2);
@@ -128,9 +141,11 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                         if (ks == SPT - 1) mma_commit(&acc_full[buf]);
                     }
                     __syncwarp();
+                    st_issue += clock64() - tt;
                 }
             }
         }
+        if (dbg && lane == 0) { p.dbg[0] = st_acc; p.dbg[1] = st_full; p.dbg[2] = st_issue; p.dbg[3] = st_a; p.dbg[4] = tit; }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ x block loader + epilogue
         const int q = warp & 3, r = q * 32 + lane;
@@ -183,26 +198,58 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                 mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);   // its x block may be replaced
                 tc_fence_after();
             }
-            {   // x block -> tensor memory: lane = row, column c holds elements k = 2c, 2c+1
-                const int m = m0 + r;
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.x + (size_t)m * XB_FEATURES);
+            const long long tl0 = clock64();
+            {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
+                // during this, so it has to be quick: a direct row-per-thread read costs one L1 wavefront per lane
+                // (12 k wavefronts per tile, ~20 k cycles).  Instead a warp reads its 32 rows coalesced, 128 bytes
+                // (= one K block) of four rows per instruction, three K blocks in flight, transposes through its
+                // staging rows and hands each thread its own row for tcgen05.st.
+                const int sub = lane >> 3, l8 = lane & 7;
+                const int mrow0 = m0 + q * 32;
+                constexpr int NBK = 3;                                   // K blocks in flight per round
 #pragma unroll 1
-                for (int c0 = 0; c0 < A_COLS; c0 += 32) {
-                    uint32_t v[32];
+                for (int kb0 = 0; kb0 < KB; kb0 += NBK) {
+                    uint4 ld[NBK][8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        uint4 t4 = (m < p.M) ? __ldg(src + c0 / 4 + i) : make_uint4(0, 0, 0, 0);
-                        v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+                    for (int b = 0; b < NBK; b++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int mm = mrow0 + 4 * i + sub;
+                            ld[b][i] = (mm < p.M) ? __ldg(reinterpret_cast<const uint4 *>(p.x + (size_t)mm * XB_FEATURES + (kb0 + b) * BK) + l8)
+                                                  : make_uint4(0, 0, 0, 0);
+                        }
+#pragma unroll
+                    for (int b = 0; b < NBK; b++) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            *reinterpret_cast<uint4 *>(stg + (4 * i + sub) * ROW_PITCH + l8 * 16) = ld[b][i];
+                        __syncwarp();
+                        uint32_t v[32];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint4 t4 = *reinterpret_cast<const uint4 *>(stg + lane * ROW_PITCH + i * 16);
+                            v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+                        }
+                        __syncwarp();
+                        tmem_st_32x32b_x32(lane_base + (kb0 + b) * (BK / 2), v);
                     }
-                    tmem_st_32x32b_x32(lane_base + c0, v);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
             }
+            if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) p.dbg[5] += clock64() - tl0;
             if (pending) epilogue(pend_m0, NT - 1, nit - 1);
             for (int nt = 0; nt < NT - 1; nt++, nit++) {
+                if (nt == NT - 8 && !p.no_prefetch) {      // next tile's x rows into L2 shortly before they are needed (G streams through L2)
+                    const int mn = m0 + (int)gridDim.x * BM + r;
+                    if (mn < p.M) {
+                        const char *nx = reinterpret_cast<const char *>(p.x + (size_t)mn * XB_FEATURES);
+#pragma unroll
+                        for (int i = 0; i < 12; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i * 128));
+                    }
+                }
                 mbar_wait(&acc_full[nit & 1], (nit >> 1) & 1);
                 tc_fence_after();
                 epilogue(m0, nt, nit);
@@ -236,6 +283,13 @@ int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float 
     p.bias = bias;
     p.out = reinterpret_cast<uint16_t *>(gates);
     p.M = M;
+    p.dbg = nullptr;
+    p.no_prefetch = getenv("XB_INPROJ_NOPF") ? 1 : 0;
+    if (getenv("XB_INPROJ_DEBUG")) {
+        static long long *d = nullptr;
+        if (!d) cudaMalloc(&d, 64);
+        p.dbg = d;
+    }
     const int ntiles = (M + BM - 1) / BM;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
     static bool configured[2][64] = {};   // per device: function attributes live in the device's context
@@ -254,5 +308,12 @@ int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float 
         inproj_kernel<false><<<grid, 256, SMEM_BYTES, s>>>(tmW, p);
     }
     XB_LAUNCH_CHECK(h);
+    if (p.dbg) {
+        long long v[6];
+        cudaDeviceSynchronize();
+        cudaMemcpy(v, p.dbg, sizeof v, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "inproj MMA thread of CTA 0: %lld tiles; stall cycles: acc_empty %lld, full %lld, a_ready %lld; issue %lld; x-block load (warp 4) %lld\n", v[4], v[0], v[1], v[3], v[2], v[5]);
+        cudaMemset(p.dbg, 0, 64);
+    }
     return XB_OK;
 }
