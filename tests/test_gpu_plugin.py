@@ -190,3 +190,38 @@ def test_read_set_pipeline_edge_cases(model5):
     (a,), _ = caller.basecall([sig])
     (b,), _ = pipeline.ReadSetBasecaller(model5, 1000, 100, 64).basecall([sig])
     assert a == b and len(a) > 0
+
+
+def test_bf16_end_to_end_identical_read_rate(golden):
+    """North-star item: with end-to-end bf16 the identical-read rate against the reference's fp32 run is reported, and
+    reads that differ do so in a few near-tie steps only (bounded edit rate).  Reference-scale weights."""
+    from make_golden import REF_SCALE
+    from xna_basecaller_b200 import util
+    cfg = sup_config(ALPHABETS[5])
+    sd = bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE)
+    sd['encoder.9.linear.weight'] = sd['encoder.9.linear.weight'] * 3.0     # SURVEY 8d: avoid the all-blank degeneracy
+    m = util.load_symbol(cfg, 'Model')(cfg)
+    m.load_state_dict(sd)
+    crf = bo.CRF(3, ALPHABETS[5])
+    rs = np.random.RandomState(21)
+    reads = [('r%d' % i, rs.randn(int(L)).astype(np.float32)) for i, L in enumerate([1000, 1700, 2350, 3100])]
+
+    def ref_scores(batch):
+        with torch.no_grad():
+            return bo.encoder_forward(sd, batch, 5)
+
+    want = {k: v['sequence'] for k, v in bo.basecall(ref_scores, crf, reads, 1000, 100, 4)}
+
+    class Read:
+        def __init__(self, rid, sig):
+            self.read_id, self.signal = rid, sig
+
+    for dtype, max_rate in ((torch.float16, 0.05), (torch.bfloat16, 0.15)):
+        mm = m.to(dtype).eval().to('cuda')
+        got = {r.read_id: res['sequence'] for r, res in
+               util.load_symbol(cfg, 'basecall')(mm, iter([Read(k, s) for k, s in reads]), chunksize=1000, overlap=100, batchsize=4)}
+        same = sum(got[k] == want[k] for k in want)
+        worst = max(_edit_distance(got[k], want[k]) / max(len(want[k]), 1) for k in want)
+        print('%s: identical-read rate %d/%d vs the fp32 reference path, worst edit rate %.3f, mean length %.0f'
+              % (dtype, same, len(want), worst, np.mean([len(v) for v in want.values()])))
+        assert worst <= max_rate
