@@ -35,6 +35,10 @@
 
 using namespace xbptx;
 
+#ifndef XB_LSTM_MUFU_TANH
+#define XB_LSTM_MUFU_TANH 1      // 0: exp/rcp activations (7 MUFU + ~45 FP ops per cell), 1: MUFU.TANH (5 MUFU + ~12)
+#endif
+
 namespace {
 
 constexpr int TILES = 24;                  // gate tiles per group
@@ -76,6 +80,12 @@ struct PLParams {
 
 #define DBG(sub_, ev) do { if (p.dbg && blockIdx.x == 0 && s >= 64 && s < 72) p.dbg[((s - 64) * 8 + (sub_)) * 16 + (ev)] = clock64(); } while (0)
 
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#if !XB_LSTM_MUFU_TANH
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -87,6 +97,7 @@ __device__ __forceinline__ float rcpf(float x) {
     return y;
 }
 __device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
+#endif
 
 template <int NS> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NS]);
 template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
@@ -300,9 +311,25 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 pre[i][0] = a0 + g01.x; pre[i][1] = a1 + g01.y; pre[i][2] = a2 + g23.x; pre[i][3] = a3 + g23.y;
             }
             // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
-            // that the MUFU latencies overlap.  Seven MUFU ops per cell: the four gate activations share one
-            // reciprocal (1/(d_i d_f d_g d_o) times the complementary products); inputs are clamped so that the
-            // product of the four denominators stays far from fp32 overflow (sigmoid(-15) = 3e-7, tanh(7.5) = 1 - 6e-7)
+            // that the MUFU latencies overlap.
+            float hout[CELLS];
+#if XB_LSTM_MUFU_TANH
+            // Five MUFU.TANH per cell (sigmoid(x) = 0.5 tanh(0.5 x) + 0.5) and a dozen FMAs: a third of the instructions
+            // of the exp/rcp form below.  tanh.approx.f32 has ~2^-11 relative error, the size of the fp16 rounding of h.
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) {
+                const float si = fmaf(tanh_approx(0.5f * pre[i][0]), 0.5f, 0.5f);
+                const float sf = fmaf(tanh_approx(0.5f * pre[i][1]), 0.5f, 0.5f);
+                const float tg = tanh_approx(pre[i][2]);
+                const float so = fmaf(tanh_approx(0.5f * pre[i][3]), 0.5f, 0.5f);
+                const float cn = fmaf(sf, cst[i], si * tg);
+                cst[i] = cn;
+                hout[i] = so * tanh_approx(cn);
+            }
+#else
+            // Seven MUFU ops per cell: the four gate activations share one reciprocal (1/(d_i d_f d_g d_o) times the
+            // complementary products); inputs are clamped so that the product of the four denominators stays far from
+            // fp32 overflow (sigmoid(-15) = 3e-7, tanh(7.5) = 1 - 6e-7)
             constexpr float L2E = 1.4426950408889634f;
             float ei[CELLS], ef[CELLS], eg[CELLS], eo[CELLS], rr[CELLS];
 #pragma unroll
@@ -330,13 +357,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             }
 #pragma unroll
             for (int i = 0; i < CELLS; i++) rr[i] = rcpf(1.f + ei[i]);
+#pragma unroll
+            for (int i = 0; i < CELLS; i++) hout[i] = eo[i] * (1.f - ei[i]) * rr[i];
+#endif
             // h slice of the warp (NS chunks x 8 units) through a 16 B-per-chunk staging row: one 16-byte global
             // store per chunk instead of eight 2-byte ones
             uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES));
 #pragma unroll
             for (int i = 0; i < CELLS; i++) {
-                const float hn = eo[i] * (1.f - ei[i]) * rr[i];
-                typename X::T hv = X::from(hn);
+                typename X::T hv = X::from(hout[i]);
                 st[(4 * i + gt) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
             }
             __syncwarp();
