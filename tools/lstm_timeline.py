@@ -17,8 +17,8 @@ buf = (ctypes.c_longlong * 1024)()
 h.lib.xb_debug_lstm_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert h.lib.xb_debug_lstm_timeline(h.h, buf) == 0
 a = np.array(buf[:]).reshape(8, 8, 16)
-names = ['poll0', 'poll1', 'tma', 'p0rdy', 'p0iss', 'p1rdy', 'p1iss', 'p2rdy', 'commit', 'e_dfull', 'e_ld', 'e_gfull', 'e_cells', 'e_red']
+names = ['poll0', 'poll1', 'tma', 'mma_rdy', 'mma_iss', '-', 'e_transp', 'e_math', '-', 'e_dfull', 'e_ld', 'e_gfull', 'e_stored', 'e_red']
 base = a[1, 0, 0]
 for s in range(1, 7):
     for sub in range(SUB):
-        print('s%d sub%d ' % (64 + s, sub) + ' '.join('%s=%d' % (n, a[s, sub, i] - base) for i, n in enumerate(names)))
+        print('s%d sub%d ' % (64 + s, sub) + ' '.join('%s=%d' % (n, a[s, sub, i] - base) for i, n in sorted(enumerate(names), key=lambda kv: a[s, sub, kv[0]]) if n != '-'))

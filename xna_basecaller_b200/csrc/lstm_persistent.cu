@@ -310,6 +310,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
                 pre[i][0] = a0 + g01.x; pre[i][1] = a1 + g01.y; pre[i][2] = a2 + g23.x; pre[i][3] = a3 + g23.y;
             }
+            if (ew == 0 && lane == 0) DBG(sub, 6);
             // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
             // that the MUFU latencies overlap.
             float hout[CELLS];
@@ -360,6 +361,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 #pragma unroll
             for (int i = 0; i < CELLS; i++) hout[i] = eo[i] * (1.f - ei[i]) * rr[i];
 #endif
+            if (ew == 0 && lane == 0) DBG(sub, 7);
             // h slice of the warp (NS chunks x 8 units) through a 16 B-per-chunk staging row: one 16-byte global
             // store per chunk instead of eight 2-byte ones
             uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES));
