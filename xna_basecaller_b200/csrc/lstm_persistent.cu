@@ -3,7 +3,7 @@
 // initial state; a reversed layer walks time backwards by indexing instead of the reference's two flips).
 //
 // Decomposition.  W_hh (3072 x 768, 4.7 MB 16-bit) does not fit one SM, so it is cut into 24 tiles of 128 gate
-// rows = 32 hidden units x [i,f,g,o] (rows are permuted at weight-load time: tile row = unit*4 + gate).  The
+// rows = 32 hidden units x [i,f,g,o] (rows are permuted at weight-load time, see "Epilogue layout").  The
 // batch is cut into G <= 6 groups; CTA (g, j) owns tile j for group g, so 24*G <= 144 CTAs are resident, one
 // per SM.
 //   - the W_hh tile lives in TENSOR MEMORY for the whole kernel (128 lanes x 384 columns, the A operand of
@@ -20,10 +20,10 @@
 //     sub-batch) counter after its stores, the TMA producer of the sub-batch acquire-polls it, proxy fence,
 //     next TMA load.  No CTA-wide barrier is on the per-step path.
 //
-// Epilogue layout.  TMEM lane r = tile row = unit*4 + gate, so the four gates of a unit sit in four adjacent
-// lanes of one warp.  A warp reads its 32 lanes x NS columns with one tcgen05.ld, transposes 4x4 blocks with
-// two rounds of xor-shuffles (lane `gate` ends up with i,f,g,o of chunk 4i+gate), and each thread updates
-// NS/4 cells.  No shared-memory staging, no named barriers.
+// Epilogue layout.  Within a TMEM lane quarter (32 rows = 8 hidden units x 4 gates) the rows are ordered gate*8 + unit.
+// tcgen05.ld.16x256b hands thread (a, b) of a warp the rows a, a+8 (and, 16 lanes further, a+16, a+24) of columns
+// 8k+2b, 8k+2b+1 -- i.e. i, f, g, o of unit a for two chunks per 8 columns: every thread receives whole cells straight
+// from tensor memory, no transpose, no shared-memory staging of the accumulator, no named barriers.
 //
 // Warp roles: warps 0..SUB-1 TMA producers (one per sub-batch: poll + loads), warp SUB MMA issuer + TMEM
 // allocator, epilogue warps start at the next multiple of four, four per sub-batch (warp % 4 = TMEM lane quarter).
@@ -99,10 +99,20 @@ __device__ __forceinline__ float rcpf(float x) {
 __device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
 #endif
 
-template <int NS> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NS]);
-template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
-template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
-
+// tcgen05.ld.16x256b.xN: 16 lanes x (N * 8) columns; thread t gets rows t/4 and t/4+8, columns 8k + 2(t%4), +1:
+// r[4k + {0,1}] = row t/4, r[4k + {2,3}] = row t/4 + 8  (layout checked on hardware: tools/tmem_layout_probe.cu)
+template <int XN> __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&r)[4 * XN]);
+template <> __device__ __forceinline__ void tmem_ld_16x256b<2>(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
 template <bool BF16, int SUB, int NS, int EW>
 __global__ void __launch_bounds__(Cfg<SUB, NS, EW>::THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
@@ -265,7 +275,6 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         const int cnt = b0 + ((sub + 1) * count) / SUB - row0;   // valid chunks of this sub-batch (<= NS)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + D_COL + sub * NS + col0;
         int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
-        const bool bit0 = lane & 1, bit1 = lane & 2;
         float cst[CELLS];
 #pragma unroll
         for (int i = 0; i < CELLS; i++) cst[i] = 0.0f;
@@ -273,42 +282,38 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         for (int s = 0; s < T; s++) {
             const int t = p.reverse ? T - 1 - s : s;
             const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * 2 + (s & 1)) * C::G_BYTES);
-            uint32_t acc[NC];
+            // Accumulator -> registers with tcgen05.ld.16x256b: thread (a = lane/4, b = lane%4) receives rows a, a+8 (first
+            // load) and a+16, a+24 (second load, 16 lanes further) of columns 8k+2b, 8k+2b+1.  The rows of a lane quarter are
+            // ordered gate*8 + unit, so those four rows are i, f, g, o of unit a: the load itself delivers whole cells
+            // (an earlier version read one row per thread and transposed with 16 shuffles per thread: 580 cycles).
+            uint32_t lo[NC / 2], hi[NC / 2];
             if (s > 0) {
                 mbar_wait(d_full(sub), (s - 1) & 1);
                 tc_fence_after();
                 if (ew == 0 && lane == 0) DBG(sub, 9);
-                tmem_ld_cols<NC>(taddr, acc);
+                tmem_ld_16x256b<NC / 8>(taddr, lo);
+                tmem_ld_16x256b<NC / 8>(taddr + (16u << 16), hi);
                 tmem_ld_wait();
                 tc_fence_before();
                 if (ew == 0 && lane == 0) DBG(sub, 10);
             } else {
 #pragma unroll
-                for (int i = 0; i < NC; i++) acc[i] = 0u;
+                for (int i = 0; i < NC / 2; i++) lo[i] = hi[i] = 0u;
             }
             mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
             if (ew == 0 && lane == 0) DBG(sub, 11);
-            // phase A: 4x4 transposes across the four lanes of a unit (lane `gt` ends with (i,f,g,o) of chunk 4i+gt);
-            // all blocks first so that the shuffles pipeline
+            // cell m of the thread: chunk 8*(m/2) + 2b + m%2 (relative to col0), unit ul
             float pre[CELLS][4];
 #pragma unroll
-            for (int i = 0; i < CELLS; i++) {
-                float a0 = __uint_as_float(acc[4 * i]), a1 = __uint_as_float(acc[4 * i + 1]);
-                float a2 = __uint_as_float(acc[4 * i + 2]), a3 = __uint_as_float(acc[4 * i + 3]);
-                float r0 = __shfl_xor_sync(0xffffffffu, bit0 ? a0 : a1, 1);
-                float r1 = __shfl_xor_sync(0xffffffffu, bit0 ? a2 : a3, 1);
-                if (bit0) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
-                pre[i][0] = a0; pre[i][1] = a1; pre[i][2] = a2; pre[i][3] = a3;
-            }
-#pragma unroll
-            for (int i = 0; i < CELLS; i++) {
-                float a0 = pre[i][0], a1 = pre[i][1], a2 = pre[i][2], a3 = pre[i][3];
-                float r0 = __shfl_xor_sync(0xffffffffu, bit1 ? a0 : a2, 2);
-                float r1 = __shfl_xor_sync(0xffffffffu, bit1 ? a1 : a3, 2);
-                if (bit1) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
-                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (col0 + 4 * i + gt) * 128 + unit * 4);
+            for (int m = 0; m < CELLS; m++) {
+                const int k4 = 4 * (m >> 1), wi = m & 1;
+                const int ch = 8 * (m >> 1) + 2 * gt + wi;
+                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (col0 + ch) * 128 + unit * 4);
                 const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
-                pre[i][0] = a0 + g01.x; pre[i][1] = a1 + g01.y; pre[i][2] = a2 + g23.x; pre[i][3] = a3 + g23.y;
+                pre[m][0] = __uint_as_float(lo[k4 + wi]) + g01.x;
+                pre[m][1] = __uint_as_float(lo[k4 + 2 + wi]) + g01.y;
+                pre[m][2] = __uint_as_float(hi[k4 + wi]) + g23.x;
+                pre[m][3] = __uint_as_float(hi[k4 + 2 + wi]) + g23.y;
             }
             if (ew == 0 && lane == 0) DBG(sub, 6);
             // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
@@ -368,7 +373,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 #pragma unroll
             for (int i = 0; i < CELLS; i++) {
                 typename X::T hv = X::from(hout[i]);
-                st[(4 * i + gt) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
+                st[(8 * (i >> 1) + 2 * gt + (i & 1)) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
             }
             __syncwarp();
             if (lane < NC && col0 + lane < cnt)

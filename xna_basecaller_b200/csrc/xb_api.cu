@@ -52,7 +52,9 @@ int dev_alloc_bytes(xb_handle *h, void **p, size_t bytes) { return dev_alloc<uin
 // mode 1: LSTM gate interleave, dst row j*128 + g*32 + u <- src row g*768 + j*32 + u;
 // mode 2: conv3 (768,16,19) -> (768, 320) with column tap*16 + ch;
 // mode 3: LSTM unit-major interleave, dst row j*128 + u*4 + g <- src row g*768 + j*32 + u (the input projection
-//         of the persistent kernel: the four gates of a unit are adjacent in a row of G).
+//         of the persistent kernel: the four gates of a unit are adjacent in a row of G);
+// mode 4: W_hh of the persistent kernel: dst row j*128 + q*32 + g*8 + ul <- src row g*768 + j*32 + q*8 + ul: within a
+//         TMEM lane quarter the rows are gate-major, which is what tcgen05.ld.16x256b hands to one thread.
 template <bool BF16>
 __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restrict__ dst, int rows_dst, int cols_dst,
                               int rows_src, int cols_src, int mode) {
@@ -69,6 +71,9 @@ __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restric
     } else if (mode == 3) {
         int j = r >> 7, u = (r >> 2) & 31, g = r & 3;
         v = src[(size_t)(g * XB_FEATURES + j * 32 + u) * cols_src + c];
+    } else if (mode == 4) {
+        int j = r >> 7, q = (r >> 5) & 3, g = (r >> 3) & 3, ul = r & 7;
+        v = src[(size_t)(g * XB_FEATURES + j * 32 + q * 8 + ul) * cols_src + c];
     } else {
         int tap = c >> 4, ch = c & 15;
         if (tap < XB_WINLEN) v = src[((size_t)r * XB_C2_CH + ch) * XB_WINLEN + tap];
@@ -273,7 +278,7 @@ int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float
     const int F = XB_FEATURES;
     const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
     if (int rc = repack(h, w_ih, h->lstm[layer].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
-    if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
+    if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, ih_mode == 3 ? 4 : 1, s)) return rc;
     lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(b_ih, b_hh, h->lstm[layer].bias, ih_mode);
     XB_LAUNCH_CHECK(h);
     h->loaded |= 2 << layer;
