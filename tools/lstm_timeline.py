@@ -17,7 +17,7 @@ buf = (ctypes.c_longlong * 1024)()
 h.lib.xb_debug_lstm_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert h.lib.xb_debug_lstm_timeline(h.h, buf) == 0
 a = np.array(buf[:]).reshape(8, 8, 16)
-names = ['poll0', 'poll1', 'tma', 'mma_rdy', 'mma_iss', '-', 'e_transp', 'e_math', '-', 'e_dfull', 'e_ld', 'e_gfull', 'e_stored', 'e_red']
+names = ['poll0', 'poll1', 'tma', 'mma_rdy', 'mma_iss', '-', 'e_transp', 'e_math', 'tma_done', 'e_dfull', 'e_ld', 'e_gfull', 'e_stored', 'e_red']
 base = a[1, 0, 0]
 for s in range(1, 7):
     for sub in range(SUB):

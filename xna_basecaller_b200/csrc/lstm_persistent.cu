@@ -222,6 +222,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                         tma_load_3d(hb + part * C::H_PART_BYTES, &tmY, h_full(sub, part), 0, tp * N + row0, part * KPB);
                     }
                     DBG(sub, 2);
+                    if (p.dbg) { mbar_wait(h_full(sub, 0), (s - 1) & 1); DBG(sub, 8); }     // pure TMA completion latency
                 }
             }
         }
