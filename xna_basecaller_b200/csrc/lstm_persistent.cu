@@ -75,6 +75,7 @@ struct PLParams {
     const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows (row = unit*4 + gate within a tile)
     uint16_t *y;                // (T, N, 768) 16-bit output = hidden states
     int *counters;              // G * SUB counters, CTR_STRIDE ints apart, zeroed before launch
+    int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
     long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
 };
 
@@ -381,11 +382,22 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
                     reinterpret_cast<const uint4 *>(st)[lane];
             if (ew == 0 && lane == 0) DBG(sub, 12);
-            __syncwarp();
-            if (lane == 0) {
-                red_release_gpu_add(ctr, 1);                  // publishes the warp's stores (cumulative over __syncwarp)
-                mbar_arrive(g_empty(sub, s & 1));
-                if (ew == 0) DBG(sub, 13);
+            if (p.one_release) {
+                // one release per sub-batch and step instead of one per warp (MEMBAR.GPU instances of one SM appear to
+                // be served one at a time): the sub-batch's warps meet at a named barrier, one thread publishes
+                named_bar_sync(1 + sub, EW * 32);
+                if (ew == 0 && lane == 0) {
+                    red_release_gpu_add(ctr, EW);             // cumulative over the barrier: all the sub-batch's stores
+                    DBG(sub, 13);
+                }
+                if (lane == 0) mbar_arrive(g_empty(sub, s & 1));
+            } else {
+                __syncwarp();
+                if (lane == 0) {
+                    red_release_gpu_add(ctr, 1);              // publishes the warp's stores (cumulative over __syncwarp)
+                    mbar_arrive(g_empty(sub, s & 1));
+                    if (ew == 0) DBG(sub, 13);
+                }
             }
         }
     }
@@ -420,6 +432,7 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
         p.w_hh = reinterpret_cast<const uint16_t *>(h->lstm[layer].w_hh);
         p.y = reinterpret_cast<uint16_t *>(y_tnc);
         p.counters = h->lstm_counters;
+        p.one_release = getenv("XB_LSTM_WARP_RELEASE") ? 0 : 1;
         p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE) : nullptr;
         XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, MAX_CTRS * CTR_STRIDE * sizeof(int), s));
         void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
@@ -451,6 +464,9 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
     if (variant == 1)
         return h->bf16 ? launch_cfg<true, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s)
                        : launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
+    if (variant == 2)
+        return h->bf16 ? launch_cfg<true, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s)
+                       : launch_cfg<false, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s);
     return h->bf16 ? launch_cfg<true, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s)
                    : launch_cfg<false, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s);
 }
