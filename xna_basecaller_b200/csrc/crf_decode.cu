@@ -45,10 +45,13 @@ template <int NFLOATS, int NT> __device__ __forceinline__ void copy_row(float *d
     for (int i = threadIdx.x; i < NFLOATS / 2; i += NT) cp_async8(dst + 2 * i, src + 2 * i);
 }
 
+// warp maximum with one integer REDUX on an order-preserving key (max is exact, so any evaluation order gives the same
+// value; +0.0f folds -0 into +0 so that the key order equals the float order)
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
+    const uint32_t bits = __float_as_uint(v + 0.0f);
+    const uint32_t key = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+    return __uint_as_float(kmax ^ ((kmax >> 31) ? 0x80000000u : 0xffffffffu));
 }
 // xor butterfly: every lane ends with the same bits (a+b == b+a), see oracle/c/crf_exact.c tree_sum()
 __device__ __forceinline__ float warp_sum_tree(float v) {
@@ -396,11 +399,17 @@ crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ b
             }
             an[c] = m;
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, off);
-            int oi = __shfl_xor_sync(0xffffffffu, besti, off);
-            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        // warp arg-max with first-index ties: one integer REDUX on an order-preserving key, then the lowest lane that
+        // holds the maximum (lanes are ordered by state, and each lane already kept its lowest edge index)
+        {
+            const uint32_t bits = __float_as_uint(best + 0.0f);                 // + 0.0f: -0 and +0 get the same key
+            const uint32_t key = act ? (bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u)) : 0u;
+            const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+            const int src_lane = __ffs(__ballot_sync(0xffffffffu, act && key == kmax)) - 1;
+            if (src_lane >= 0) {
+                best = __shfl_sync(0xffffffffu, best, src_lane);
+                besti = __shfl_sync(0xffffffffu, besti, src_lane);
+            }
         }
         if (lane == 0) { bval[(t & 1) * W + w] = best; bidx[(t & 1) * W + w] = besti; }
     }
