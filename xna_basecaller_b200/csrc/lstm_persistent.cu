@@ -11,22 +11,26 @@
 //   - a group is cut again into SUB sub-batches of <= NS chunks that run the recurrence independently and out
 //     of phase: the serial chain of one step (h exchange through L2, TMA, MMA, cell update) is several times
 //     longer than its tensor-pipe time, so the other sub-batches fill the pipe meanwhile;
-//   - per step and sub-batch the CTA loads h_{t-1} (NS x 768) with HP 3-D TMA boxes (128B swizzle; the B
-//     operand; the MMAs of a box start as soon as it lands), issues 48 tcgen05.mma (M=128 gate rows, N=NS
-//     chunks, K=16) into an NS-column fp32 accumulator in TMEM, adds the hoisted input projection G[t]
-//     (TMA-prefetched one step ahead), applies the cell update with the fp32 cell state held in registers, and
-//     writes its 32-unit slice of h_t to HBM;
-//   - the 24 CTAs of a group exchange h_t through L2: every epilogue warp release-adds a per-(group,
-//     sub-batch) counter after its stores, the TMA producer of the sub-batch acquire-polls it, proxy fence,
+//   - per step and sub-batch the CTA loads h_{t-1} (NS x 768) with one 3-D TMA box (128B swizzle; the B
+//     operand), issues 48 tcgen05.mma (M=128 gate rows, N=NS chunks, K=16) into an NS-column fp32 accumulator
+//     in TMEM, adds the hoisted input projection G[t] (TMA-prefetched one step ahead), applies the cell update
+//     (MUFU.TANH activations) with the fp32 cell state held in registers, and writes its 32-unit slice of h_t;
+//   - the 24 CTAs of a group exchange h_t through L2: after their stores the epilogue warps of a sub-batch meet
+//     at a named barrier and ONE thread release-adds a per-(group, sub-batch) counter (one MEMBAR.GPU per
+//     sub-batch and step: fences issued by several warps of an SM are served one after the other, eight of
+//     them cost 1.4 ms per batch); the TMA producer of the sub-batch polls the counter with relaxed loads (the
+//     only reader of the data is the TMA unit, issued after the poll and reading L2 directly), proxy fence,
 //     next TMA load.  No CTA-wide barrier is on the per-step path.
 //
 // Epilogue layout.  Within a TMEM lane quarter (32 rows = 8 hidden units x 4 gates) the rows are ordered gate*8 + unit.
 // tcgen05.ld.16x256b hands thread (a, b) of a warp the rows a, a+8 (and, 16 lanes further, a+16, a+24) of columns
 // 8k+2b, 8k+2b+1 -- i.e. i, f, g, o of unit a for two chunks per 8 columns: every thread receives whole cells straight
-// from tensor memory, no transpose, no shared-memory staging of the accumulator, no named barriers.
+// from tensor memory, no transpose and no shared-memory staging of the accumulator.
 //
 // Warp roles: warps 0..SUB-1 TMA producers (one per sub-batch: poll + loads), warp SUB MMA issuer + TMEM
-// allocator, epilogue warps start at the next multiple of four, four per sub-batch (warp % 4 = TMEM lane quarter).
+// allocator, epilogue warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
+// quarter; the second four take the upper half of the chunk columns).  XB_LSTM_VARIANT selects the measured
+// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks), XB_LSTM_WARP_RELEASE=1 the per-warp release.
 #include <stdlib.h>
 
 #include "xb_common.cuh"
@@ -72,7 +76,7 @@ template <int SUB, int NS, int EW> struct Cfg {          // EW = epilogue warps 
 struct PLParams {
     int T, N, reverse;
     int batch0, nbatch, G;      // batch rows [batch0, batch0 + nbatch) are split into G groups
-    const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows (row = unit*4 + gate within a tile)
+    const uint16_t *w_hh;       // (3072, 768) 16-bit, tile-permuted rows (repack mode 4 in xb_api.cu)
     uint16_t *y;                // (T, N, 768) 16-bit output = hidden states
     int *counters;              // G * SUB counters, CTR_STRIDE ints apart, zeroed before launch
     int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
