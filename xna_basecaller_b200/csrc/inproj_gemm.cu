@@ -61,8 +61,8 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;      // [2]
     uint64_t *acc_empty = acc_full + 2;       // [2]
-    uint64_t *a_ready = acc_empty + 2;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(a_ready + 1);
+    uint64_t *a_ready = acc_empty + 2;        // [SPT]: K blocks ks*KPS .. ks*KPS+KPS-1 of the x block are in tensor memory
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(a_ready + SPT);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int ntiles = (p.M + BM - 1) / BM;
@@ -77,7 +77,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 4);
         }
-        mbar_init(a_ready, 4);
+        for (int ks = 0; ks < SPT; ks++) mbar_init(&a_ready[ks], 4);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -110,10 +110,6 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         long long st_acc = 0, st_full = 0, st_issue = 0, st_a = 0, tt;
         const bool dbg = p.dbg && blockIdx.x == 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tit++) {
-            tt = clock64();
-            mbar_wait(a_ready, tit & 1);                       // x block of this tile is in tensor memory
-            tc_fence_after();
-            st_a += clock64() - tt;
             for (int nt = 0; nt < NT; nt++, nit++) {
                 const int buf = nit & 1;
                 tt = clock64();
@@ -127,6 +123,12 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
                     st_full += clock64() - tt;
+                    if (nt == 0) {                             // first N tile: the x block arrives K-block group by group
+                        tt = clock64();
+                        mbar_wait(&a_ready[ks], tit & 1);
+                        tc_fence_after();
+                        st_a += clock64() - tt;
+                    }
                     tt = clock64();
                     if (elect_one()) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
@@ -202,11 +204,11 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
             {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
                 // during this, so it has to be quick: a direct row-per-thread read costs one L1 wavefront per lane
                 // (12 k wavefronts per tile, ~20 k cycles).  Instead a warp reads its 32 rows coalesced, 128 bytes
-                // (= one K block) of four rows per instruction, three K blocks in flight, transposes through its
+                // (= one K block) of four rows per instruction, four K blocks in flight, transposes through its
                 // staging rows and hands each thread its own row for tcgen05.st.
                 const int sub = lane >> 3, l8 = lane & 7;
                 const int mrow0 = m0 + q * 32;
-                constexpr int NBK = 3;                                   // K blocks in flight per round
+                constexpr int NBK = KPS;                                 // K blocks in flight per round = one MMA stage
 #pragma unroll 1
                 for (int kb0 = 0; kb0 < KB; kb0 += NBK) {
                     uint4 ld[NBK][8];
@@ -233,11 +235,11 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                         __syncwarp();
                         tmem_st_32x32b_x32(lane_base + (kb0 + b) * (BK / 2), v);
                     }
+                    tmem_st_wait();                            // the MMAs of the first N tile start on this group at once
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[kb0 / KPS]);
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);
             }
             if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) p.dbg[5] += clock64() - tl0;
             if (pending) epilogue(pend_m0, NT - 1, nit - 1);
