@@ -17,8 +17,10 @@
  * no contraction; exp/log from xb_exact_math.h):
  *   logsumexp over the NZ edges of a state:  m = max_k x_k;  s = (..(e_0 + e_1) + ..) + e_{NZ-1},
  *       e_k = exp(x_k - m);  result = m + log(s).   Backward (beta) edge order: stay, then moves j = 0..n-1.
- *   softmax over all C*NZ edges of a step: gmax = max; e = exp(x - gmax); per state s_c = sum_k e (k order);
- *       S = tree_sum(s_c) (below); p = e * (1 / S);  lp = log(p + 1e-8).
+ *   softmax over all C*NZ edges of a step, factored per SOURCE state s: z = M + beta_{t+1}[dst] over the edges leaving
+ *       s (stay, then moves), m_s = max z, w = exp(z - m_s) (shared with Log-beta_t[s] = m_s + log(sum w));
+ *       g_s = m_s + alpha_t[s], gmax = max_s g_s, f_s = exp(g_s - gmax); numerator e = w * f_src; per destination
+ *       state s_c = sum_k e (k order); S = tree_sum(s_c) (below); p = e * (1 / S);  lp = log(p + 1e-8).
  *   tree_sum over states: state c sits in lane c%32 of warp c/32 (missing lanes contribute +0); each warp
  *       does the xor-butterfly v_i += v_{i^off}, off = 16,8,4,2,1; warp totals are added in warp order.
  *   arg-max over the flat edge index c*NZ+k: strictly greater wins, i.e. first index on ties.
@@ -169,7 +171,8 @@ int xbo_crf_decode_range(const float *scores, int T, int N, int n_begin, int n_e
     float *lp = (float *)malloc((size_t)T * S * sizeof(float));
     float *x = (float *)malloc(S * sizeof(float));
     float *sc = (float *)malloc(L.C * sizeof(float));
-    if (!alpha || !bmax || !lp || !x || !sc) return -2;
+    float *gs = (float *)malloc(L.C * sizeof(float));
+    if (!alpha || !bmax || !lp || !x || !sc || !gs) return -2;
     for (int n = n_begin; n < n_end; n++) {
         for (int c = 0; c < L.C; c++) alpha[c] = 0.0f;
         for (int t = 0; t < T; t++)
@@ -179,17 +182,36 @@ int xbo_crf_decode_range(const float *scores, int T, int N, int n_begin, int n_e
         for (int t = T - 1; t >= 0; t--) {
             const float *M = scores + ((size_t)t * N + n) * S, *a = alpha + (size_t)t * L.C;
             const float *b1 = beta[(t + 1) & 1];
+            /* Edges grouped by SOURCE state s (stay, then the moves j = 0..n-1): z = M + beta_{t+1}[dst],
+             * m_s = max z, w = exp(z - m_s): sum_w gives Log-beta_t[s], and the softmax numerator of an edge factors
+             * as exp(x - gmax) = w * f_s with x = z + alpha_t[s], f_s = exp((m_s + alpha_t[s]) - gmax): one exp per
+             * state instead of one per edge for the posterior path. */
             float gmax = 0.0f;
-            for (int c = 0; c < L.C; c++)
-                for (int k = 0; k < L.NZ; k++) {
-                    float v = XB_ADD(XB_ADD(M[c * L.NZ + k], a[src_state(&L, c, k)]), b1[c]);
-                    x[c * L.NZ + k] = v;
-                    gmax = (c == 0 && k == 0) || v > gmax ? v : gmax;
+            float *bt = beta[t & 1];
+            for (int sp = 0; sp < L.C; sp++) {
+                float z[MAXNZ], m;
+                int kk = 1 + sp / L.n_pow, base = (sp % L.n_pow) * L.n;
+                z[0] = XB_ADD(M[sp * L.NZ], b1[sp]);
+                m = z[0];
+                for (int j = 0; j < L.n; j++) {
+                    z[1 + j] = XB_ADD(M[(base + j) * L.NZ + kk], b1[base + j]);
+                    m = z[1 + j] > m ? z[1 + j] : m;
                 }
+                float sy = 0.0f;
+                for (int j = 0; j < L.NZ; j++) {
+                    float w = xb_expf(XB_SUB(z[j], m));
+                    x[j == 0 ? sp * L.NZ : (base + j - 1) * L.NZ + kk] = w;
+                    sy = (j == 0) ? w : XB_ADD(sy, w);
+                }
+                bt[sp] = lse_finish(m, sy);
+                gs[sp] = XB_ADD(m, a[sp]);
+                gmax = (sp == 0 || gs[sp] > gmax) ? gs[sp] : gmax;
+            }
+            for (int sp = 0; sp < L.C; sp++) gs[sp] = xb_expf(XB_SUB(gs[sp], gmax));      /* f_s */
             for (int c = 0; c < L.C; c++) {
                 float s = 0.0f;
                 for (int k = 0; k < L.NZ; k++) {
-                    float e = xb_expf(XB_SUB(x[c * L.NZ + k], gmax));
+                    float e = XB_MUL(x[c * L.NZ + k], gs[src_state(&L, c, k)]);
                     x[c * L.NZ + k] = e;
                     s = (k == 0) ? e : XB_ADD(s, e);
                 }
@@ -203,12 +225,11 @@ int xbo_crf_decode_range(const float *scores, int T, int N, int n_begin, int n_e
                 lpt[i] = xb_logf(XB_ADD(p, XB_POST_EPS));
             }
             if (lp_out) memcpy(lp_out + ((size_t)t * N + n) * S, lpt, S * sizeof(float));
-            beta_step(&L, M, b1, beta[t & 1], 0);
             beta_step(&L, lpt, bmax + (size_t)(t + 1) * L.C, bmax + (size_t)t * L.C, 1);
         }
         viterbi_forward(&L, lp, S, bmax, T, labels + (size_t)n * T);
     }
-    free(alpha); free(bmax); free(lp); free(x); free(sc);
+    free(alpha); free(bmax); free(lp); free(x); free(sc); free(gs);
     return 0;
 }
 

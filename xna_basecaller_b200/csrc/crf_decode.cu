@@ -212,6 +212,7 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
     float *beta = ringA + D * NT;        // 2 * NT
     float *bm = beta + 2 * NT;           // 2 * NT
     float *red = bm + 2 * NT;            // 2 * W
+    float *FS = red + 2 * W;             // NT
     const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
     const bool act = c < C;
     const float *base = scores + (size_t)n * S;
@@ -255,36 +256,42 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
         const float *m1 = bm + (i & 1) * NT;
         float *m0 = bm + ((i + 1) & 1) * NT;
 
-        float x[NZ], lmax = -INFINITY;
+        // Thread c as SOURCE state: z over the edges leaving c (stay, then the n_base moves), w = exp(z - m_c) feeds
+        // both Log beta_t[c] and the softmax numerator exp(x - gmax) = w * f_c, f_c = exp((m_c + alpha_t[c]) - gmax).
+        float g = -INFINITY;
         if (act) {
-            const float bc = b1[c];
-#pragma unroll
-            for (int k = 0; k < NZ; k++) {
-                x[k] = XB_ADD(XB_ADD(M[c * NZ + k], A[src[k]]), bc);
-                lmax = fmaxf(lmax, x[k]);
-            }
-            // Log beta_t[c]: edges leaving c = stay, then the n_base moves
-            float y[NZ], m;
-            y[0] = XB_ADD(M[c * NZ], bc);
-            m = y[0];
+            float z[NZ], m;
+            z[0] = XB_ADD(M[c * NZ], b1[c]);
+            m = z[0];
 #pragma unroll
             for (int j = 0; j < NB; j++) {
-                y[1 + j] = XB_ADD(M[(cb + j) * NZ + kk], b1[cb + j]);
-                m = fmaxf(m, y[1 + j]);
+                z[1 + j] = XB_ADD(M[(cb + j) * NZ + kk], b1[cb + j]);
+                m = fmaxf(m, z[1 + j]);
             }
-            b0[c] = lse_exact<NZ>(y, m);
+            float sy = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NZ; j++) {
+                float e = xb_expf_le0(XB_SUB(z[j], m));
+                LP[j == 0 ? c * NZ : (cb + j - 1) * NZ + kk] = e;
+                sy = (j == 0) ? e : XB_ADD(sy, e);
+            }
+            b0[c] = XB_ADD(m, xb_logf_norm(sy));
+            g = XB_ADD(m, A[c]);
         }
-        float wm = warp_max(lmax);
+        float wm = warp_max(g);
         if (lane == 0) red[w] = wm;
         __syncthreads();                                                        // B1
         float gmax = red[0];
 #pragma unroll
         for (int j = 1; j < W; j++) gmax = fmaxf(gmax, red[j]);
-        float s = 0.0f;
+        if (act) FS[c] = xb_expf_le0(XB_SUB(g, gmax));
+        __syncthreads();                                                        // B1b
+        // Thread c as DESTINATION state: numerators of its NZ incoming edges.
+        float x[NZ], s = 0.0f;
         if (act) {
 #pragma unroll
             for (int k = 0; k < NZ; k++) {
-                x[k] = xb_expf_le0(XB_SUB(x[k], gmax));
+                x[k] = XB_MUL(LP[c * NZ + k], FS[src[k]]);
                 s = (k == 0) ? x[k] : XB_ADD(s, x[k]);
             }
         }
@@ -469,7 +476,7 @@ template <int NB, int SL> size_t smem_bscan() {
 }
 template <int NB, int SL> size_t smem_backward() {
     using L = Lat<NB, SL>;
-    return sizeof(float) * (L::D * L::S + L::S + L::D * L::NT + 4 * L::NT + 2 * L::W);
+    return sizeof(float) * (L::D * L::S + L::S + L::D * L::NT + 5 * L::NT + 2 * L::W);
 }
 template <int NB, int SL> size_t smem_vit(int T) {
     using L = Lat<NB, SL>;
