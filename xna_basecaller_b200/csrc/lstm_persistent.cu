@@ -27,8 +27,9 @@
 // 8k+2b, 8k+2b+1 -- i.e. i, f, g, o of unit a for two chunks per 8 columns: every thread receives whole cells straight
 // from tensor memory, no transpose and no shared-memory staging of the accumulator.
 //
-// Warp roles: warps 0..SUB-1 TMA producers (one per sub-batch: poll + loads), warp SUB MMA issuer + TMEM
-// allocator, epilogue warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
+// Warp roles: warps 0..SUB-1 drive one sub-batch each (one elected thread: counter poll, h boxes, then the step's
+// MMAs part by part as the boxes land, commit; plus the G prefetch), warp SUB allocates tensor memory, epilogue
+// warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
 // quarter; the second four take the upper half of the chunk columns).  XB_LSTM_VARIANT selects the measured
 // alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks), XB_LSTM_WARP_RELEASE=1 the per-warp release.
 #include <stdlib.h>
@@ -47,8 +48,8 @@ namespace {
 
 constexpr int TILES = 24;                  // gate tiles per group
 constexpr int KCH = XB_FEATURES / 64;      // 12 K blocks of 64
-constexpr int HP = 1;                      // h boxes per step (one 3-D box: several smaller boxes are served one after
-                                           // the other by the TMA unit, ~800 cycles each, and arrive later in total)
+constexpr int HP = 3;                      // h boxes per step: the MMAs of a box start when it lands (measured 1: 15.3,
+                                           // 2: 14.9, 3: 14.8, 4: 15.4, 6: 15.4 ms per batch for the five layers)
 constexpr int KPB = KCH / HP;              // K blocks per box
 constexpr int D_COL = 384;                 // accumulators start after the 384 columns of W_hh
 constexpr int CTR_STRIDE = 32;             // ints between counters (one 128-byte line each)
@@ -80,6 +81,7 @@ struct PLParams {
     uint16_t *y;                // (T, N, 768) 16-bit output = hidden states
     int *counters;              // G * SUB counters, CTR_STRIDE ints apart, zeroed before launch
     int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
+    int prefetch_y;             // d > 0: prefetch the y rows of step s+d into L2
     long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
 };
 
@@ -195,8 +197,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         if (elect_one()) {
             const int sub = warp;
             const int row0 = sub_row0(sub);
+            const int cnt_sub = b0 + ((sub + 1) * count) / SUB - row0;
             const int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
             uint8_t *hb = hbuf + sub * C::H_BYTES;
+            constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, 128, NS);
+            const uint64_t bdesc0 = umma_desc_sw128(smem_u32(hb));
+            const uint32_t dcol = tmem_base + D_COL + sub * NS;
             mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
             tma_load_2d(gbuf + (sub * 2) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
             for (int s = 0; s < T; s++) {
@@ -207,6 +213,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     if (u >= 1) mbar_wait(g_empty(sub, q), (u - 1) & 1);
                     mbar_expect_tx(g_full(sub, q), C::G_BYTES);
                     tma_load_2d(gbuf + (sub * 2 + q) * C::G_BYTES, &tmG, g_full(sub, q), j * 128, tn * N + row0);
+                }
+                if (p.prefetch_y && s + p.prefetch_y < T) {
+                    // bring the y rows this sub-batch will write two steps from now into L2 (one row per CTA and sub-batch,
+                    // round robin over the group's tiles): a 16-byte store to a line that is not resident is only
+                    // acknowledged after the line was fetched from HBM, which is what the release below waits for
+                    const int t2 = p.reverse ? T - 1 - (s + p.prefetch_y) : s + p.prefetch_y;
+                    for (int r = j; r < cnt_sub; r += TILES)
+                        prefetch_l2_bulk(p.y + ((size_t)t2 * N + row0 + r) * XB_FEATURES, XB_FEATURES * 2);
                 }
                 if (s > 0) {
                     const int tp = p.reverse ? t + 1 : t - 1;
@@ -227,45 +241,25 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                         tma_load_3d(hb + part * C::H_PART_BYTES, &tmY, h_full(sub, part), 0, tp * N + row0, part * KPB);
                     }
                     DBG(sub, 2);
-                    if (p.dbg) { mbar_wait(h_full(sub, 0), (s - 1) & 1); DBG(sub, 8); }     // pure TMA completion latency
-                }
-            }
-        }
-    } else if (warp == SUB) {
-        // ------------------------------------------------------------------ MMA issuer: serve whichever sub-batch
-        // has its next h box in shared memory (no head-of-line blocking between the independent chains)
-        constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, 128, NS);
-        const uint32_t hb = smem_u32(hbuf);
-        int step[SUB], part[SUB];
+                    // ... and the MMAs of the step, part by part as the boxes land (blocking try_wait: ~60 cycles from
+                    // completion to wake-up; an earlier single MMA warp scanning all sub-batches with test_wait paid
+                    // ~150 cycles per probe and could not keep up with more than one box per step)
 #pragma unroll
-        for (int i = 0; i < SUB; i++) { step[i] = 1; part[i] = 0; }
-        int remaining = (T > 1) ? SUB : 0;
-        while (remaining > 0) {
+                    for (int part = 0; part < HP; part++) {
+                        mbar_wait(h_full(sub, part), (s - 1) & 1);
+                        tc_fence_after();
+                        if (part == 0) DBG(sub, 8);
+                        if (part == 0) DBG(sub, 3);
 #pragma unroll
-            for (int sub = 0; sub < SUB; sub++) {
-                if (step[sub] >= T) continue;
-                const int s = step[sub];
-                const int ready = mbar_test_wait(h_full(sub, part[sub]), (s - 1) & 1) ? 1 : 0;
-                if (!__shfl_sync(0xffffffffu, ready, 0)) continue;
-                tc_fence_after();
-                if (elect_one()) {
-                    DBG(sub, 3 + 2 * part[sub]);
-                    const uint64_t bdesc0 = umma_desc_sw128(hb + sub * C::H_BYTES + part[sub] * C::H_PART_BYTES);
-                    const uint32_t a0 = tmem_base + part[sub] * (KPB * 32);
-                    const uint32_t d = tmem_base + D_COL + sub * NS;
-#pragma unroll
-                    for (int kk = 0; kk < KPB * 4; kk++) {
-                        const int kc = kk >> 2, k = kk & 3;
-                        mma_f16_ts(d, a0 + kk * 8, bdesc0 + (uint64_t)((kc * C::H_BLOCK_BYTES + k * 32) >> 4), idesc,
-                                   (part[sub] | kk) != 0);
+                        for (int kk = 0; kk < KPB * 4; kk++) {
+                            const int kc = kk >> 2, k = kk & 3;
+                            mma_f16_ts(dcol, tmem_base + part * (KPB * 32) + kk * 8,
+                                       bdesc0 + (uint64_t)((part * C::H_PART_BYTES + kc * C::H_BLOCK_BYTES + k * 32) >> 4), idesc,
+                                       (part | kk) != 0);
+                        }
                     }
-                    if (part[sub] == HP - 1) mma_commit(d_full(sub));
-                    DBG(sub, 4 + 2 * part[sub]);
-                }
-                __syncwarp();
-                if (++part[sub] == HP) {
-                    part[sub] = 0;
-                    if (++step[sub] >= T) remaining--;
+                    mma_commit(d_full(sub));
+                    DBG(sub, 4);
                 }
             }
         }
@@ -292,8 +286,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             // load) and a+16, a+24 (second load, 16 lanes further) of columns 8k+2b, 8k+2b+1.  The rows of a lane quarter are
             // ordered gate*8 + unit, so those four rows are i, f, g, o of unit a: the load itself delivers whole cells
             // (an earlier version read one row per thread and transposed with 16 shuffles per thread: 580 cycles).
-            uint32_t lo[NC / 2], hi[NC / 2];
+            // The input projection of the step arrived a step ago: fetch it from shared memory BEFORE waiting for the
+            // accumulator, so only the adds remain on the serial chain.
+            // cell m of the thread: chunk 8*(m/2) + 2b + m%2 (relative to col0), unit ul
+            mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
+            float pre[CELLS][4];
+#pragma unroll
+            for (int m = 0; m < CELLS; m++) {
+                const int ch = 8 * (m >> 1) + 2 * gt + (m & 1);
+                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (col0 + ch) * 128 + unit * 4);
+                const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
+                pre[m][0] = g01.x; pre[m][1] = g01.y; pre[m][2] = g23.x; pre[m][3] = g23.y;
+            }
+            if (ew == 0 && lane == 0) DBG(sub, 11);
             if (s > 0) {
+                uint32_t lo[NC / 2], hi[NC / 2];
                 mbar_wait(d_full(sub), (s - 1) & 1);
                 tc_fence_after();
                 if (ew == 0 && lane == 0) DBG(sub, 9);
@@ -302,24 +309,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 tmem_ld_wait();
                 tc_fence_before();
                 if (ew == 0 && lane == 0) DBG(sub, 10);
-            } else {
 #pragma unroll
-                for (int i = 0; i < NC / 2; i++) lo[i] = hi[i] = 0u;
-            }
-            mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
-            if (ew == 0 && lane == 0) DBG(sub, 11);
-            // cell m of the thread: chunk 8*(m/2) + 2b + m%2 (relative to col0), unit ul
-            float pre[CELLS][4];
-#pragma unroll
-            for (int m = 0; m < CELLS; m++) {
-                const int k4 = 4 * (m >> 1), wi = m & 1;
-                const int ch = 8 * (m >> 1) + 2 * gt + wi;
-                const uint2 graw = *reinterpret_cast<const uint2 *>(Gs + (col0 + ch) * 128 + unit * 4);
-                const float2 g01 = X::unpack(graw.x), g23 = X::unpack(graw.y);
-                pre[m][0] = __uint_as_float(lo[k4 + wi]) + g01.x;
-                pre[m][1] = __uint_as_float(lo[k4 + 2 + wi]) + g01.y;
-                pre[m][2] = __uint_as_float(hi[k4 + wi]) + g23.x;
-                pre[m][3] = __uint_as_float(hi[k4 + 2 + wi]) + g23.y;
+                for (int m = 0; m < CELLS; m++) {
+                    const int k4 = 4 * (m >> 1), wi = m & 1;
+                    pre[m][0] += __uint_as_float(lo[k4 + wi]);
+                    pre[m][1] += __uint_as_float(lo[k4 + 2 + wi]);
+                    pre[m][2] += __uint_as_float(hi[k4 + wi]);
+                    pre[m][3] += __uint_as_float(hi[k4 + 2 + wi]);
+                }
             }
             if (ew == 0 && lane == 0) DBG(sub, 6);
             // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
@@ -437,6 +434,7 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
         p.y = reinterpret_cast<uint16_t *>(y_tnc);
         p.counters = h->lstm_counters;
         p.one_release = getenv("XB_LSTM_WARP_RELEASE") ? 0 : 1;
+        p.prefetch_y = getenv("XB_LSTM_PREFETCH_Y") ? atoi(getenv("XB_LSTM_PREFETCH_Y")) : 4;
         p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE) : nullptr;
         XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, MAX_CTRS * CTR_STRIDE * sizeof(int), s));
         void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
