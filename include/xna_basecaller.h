@@ -127,6 +127,16 @@ int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, 
 int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets,
                         int Lmax, const int32_t *lengths, int normalise, float *loss, void *stream);
 
+/* Backward of the above (what loss.backward() propagates to the scores in Trainer.train_one_step,
+ * training.py:91-117, through seqdist's Logspace gradients): grad_scores (T, N, C*NZ) fp32 =
+ * grad_loss[n] * (P_full[t,n,e] * normalise - P_target[t,n,e]) / lengths[n], P_full the edge posteriors of the
+ * whole lattice, P_target those of the target's alignment lattice.  grad_loss (N) fp32 is the upstream gradient
+ * per sequence (1/N for reduction='mean'); alpha_ws is caller-owned scratch of (T+1) * N * (Lmax - state_len + 1)
+ * floats. */
+int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets,
+                        int Lmax, const int32_t *lengths, int normalise, const float *grad_loss,
+                        float *alpha_ws, float *grad_scores, void *stream);
+
 /* util.stitch over left-packed chunks (util.py:169-188; crf/basecall.py:15-24): for each read r,
  * concatenates slices of its chunks' packed rows.  chunk_first[r], chunk_count[r], read_len[r]
  * (samples) describe the reads; rows are (n_chunks_total, T) int8; out is (n_reads, out_stride) int8,

@@ -27,4 +27,4 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden():
     import numpy as np
-    return {name: np.load(os.path.join(GOLDEN, name + '.npz')) for name in ('crf', 'encoder', 'stitch', 'basecall')}
+    return {name: np.load(os.path.join(GOLDEN, name + '.npz')) for name in ('crf', 'crf_grad', 'encoder', 'stitch', 'basecall')}

@@ -49,9 +49,28 @@ def synthetic_signal(seed, N, L):
     return torch.randn(N, 1, L, generator=g)
 
 
+def make_crf_grad(RM):
+    """Gradient of the reference's CTC_CRF.ctc_loss w.r.t. the scores (autograd through the restated seqdist), sub-sampled."""
+    out = {}
+    for n_base, alphabet in ALPHABETS.items():
+        sd = RM.CTC_CRF(3, alphabet)
+        for seed in (0, 1):
+            s = synthetic_scores(seed, 160, 3, n_base).requires_grad_()
+            tg, tl = synthetic_targets(100 + seed, 3, n_base, 30, 50)
+            sd.ctc_loss(s, tg, tl).backward()                      # reduction='mean', normalise_scores=True
+            key = 'n%d_s%d_' % (n_base, seed)
+            out[key + 'grad_sub'] = s.grad[::9, :, ::7].numpy()
+            out[key + 'grad_abs_rowsum'] = s.grad.abs().sum(2).numpy()
+    np.savez_compressed(os.path.join(OUT, 'crf_grad.npz'), **out)
+    print('crf_grad.npz', os.path.getsize(os.path.join(OUT, 'crf_grad.npz')))
+
+
 def main():
     mods = refshim.install()
     RM, RU, RB = mods['bonito.crf.model'], mods['bonito.util'], mods['bonito.crf.basecall']
+    if '--only-crf-grad' in sys.argv:
+        return make_crf_grad(RM)
+    make_crf_grad(RM)
 
     # ---- (i)+(ii) CRF: reference CTC_CRF methods on synthetic scores
     crf = {}

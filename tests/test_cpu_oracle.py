@@ -61,6 +61,22 @@ def test_crf_restatement_matches_reference_golden(golden, n_base, seed):
 
 
 @pytest.mark.parametrize('n_base', [4, 5, 6])
+def test_oracle_ctc_loss_gradient_matches_reference_golden(golden, n_base):
+    """d ctc_loss / d scores of the restated path == the reference class's autograd result, and equals the closed form
+    (P_full - P_target) / (N * len) the CUDA backward kernel implements (rows sum to 0: both posteriors sum to 1)."""
+    g = golden['crf_grad']
+    crf = bo.CRF(3, ALPHABETS[n_base])
+    for seed in (0, 1):
+        s = synthetic_scores(seed, 160, 3, n_base).requires_grad_()
+        tg, tl = synthetic_targets(100 + seed, 3, n_base, 30, 50)
+        crf.ctc_loss(s, tg, tl).backward()
+        key = 'n%d_s%d_' % (n_base, seed)
+        np.testing.assert_allclose(s.grad[::9, :, ::7].numpy(), g[key + 'grad_sub'], rtol=5e-4, atol=5e-7)
+        np.testing.assert_allclose(s.grad.abs().sum(2).numpy(), g[key + 'grad_abs_rowsum'], rtol=1e-4)
+        assert s.grad.sum(2).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize('n_base', [4, 5, 6])
 def test_c_checker_matches_reference_golden(golden, n_base):
     """The bit-exact C checker decodes the golden inputs to exactly the reference's paths and strings."""
     g = golden['crf']

@@ -124,6 +124,38 @@ def test_ctc_loss_long_targets(handles):
     np.testing.assert_allclose(h.ctc_loss(s, tg, tl).cpu().numpy(), ref.numpy(), rtol=5e-5)
 
 
+@pytest.mark.parametrize('n_base', [4, 5, 6])
+def test_ctc_loss_backward_matches_reference_golden(handles, golden, n_base):
+    """xb_ctc_crf_loss_bwd with grad_loss = 1/N (reduction='mean') against the gradient autograd gives the reference class."""
+    h = handles[n_base]
+    g = golden['crf_grad']
+    for seed in (0, 1):
+        s = synthetic_scores(seed, 160, 3, n_base)
+        tg, tl = synthetic_targets(100 + seed, 3, n_base, 30, 50)
+        grad = h.ctc_loss_bwd(s, tg, tl, torch.full((3,), 1.0 / 3)).cpu()
+        key = 'n%d_s%d_' % (n_base, seed)
+        np.testing.assert_allclose(grad[::9, :, ::7].numpy(), g[key + 'grad_sub'], rtol=5e-4, atol=5e-7)
+        np.testing.assert_allclose(grad.abs().sum(2).numpy(), g[key + 'grad_abs_rowsum'], rtol=1e-3)
+
+
+@pytest.mark.parametrize('normalise', [True, False])
+def test_ctc_loss_backward_weighted_long_targets(handles, normalise):
+    """Per-sequence upstream gradients (incl. 0 = a clipped loss, and a negative one), T = 800, targets of 350-450 bases
+    with repeated k-mers (several positions scatter into one edge), against autograd through the oracle."""
+    n_base = 5
+    h = handles[n_base]
+    s = synthetic_scores(5, 800, 4, n_base)
+    tg, tl = synthetic_targets(9, 4, n_base, 350, 450)
+    w = torch.tensor([1.0, 0.0, -0.5, 0.25])
+    sr = s.clone().requires_grad_()
+    loss = bo.CRF(3, ALPHABETS[n_base]).ctc_loss(sr, tg, tl, reduction='none', normalise_scores=normalise)
+    (loss * w).sum().backward()
+    grad = h.ctc_loss_bwd(s, tg, tl, w, normalise=normalise).cpu()
+    # alpha + beta - logz is a difference of numbers ~1e3 in fp32: ~1e-3 relative on posteriors <= |w| / len ~ 3e-3
+    assert (grad - sr.grad).abs().max().item() < 2e-5
+    assert grad[:, 1].abs().max().item() == 0.0
+
+
 def test_stitch_matches_reference_golden(handles, golden):
     h = handles[5]
     g = golden['stitch']

@@ -134,6 +134,26 @@ def test_ctc_crf_methods(model5, golden):
     np.testing.assert_allclose((sd.normalise(s)).cpu().numpy(), bo.CRF(3, ALPHABETS[5]).normalise(s.cpu()).numpy(), atol=1e-4)
 
 
+def test_ctc_loss_backward_through_plugin(model5, golden):
+    """CTC_CRF.ctc_loss is differentiable w.r.t. the scores like the reference's (training.py:100-108 calls
+    loss.backward()); loss_clip zeroes the gradient of clipped sequences through ordinary autograd."""
+    from make_golden import synthetic_scores, synthetic_targets
+    sd = model5.seqdist
+    s = synthetic_scores(0, 160, 3, 5).cuda().requires_grad_()
+    tg, tl = synthetic_targets(100, 3, 5, 30, 50)
+    sd.ctc_loss(s, tg.cuda(), tl.cuda()).backward()
+    g = golden['crf_grad']
+    np.testing.assert_allclose(s.grad[::9, :, ::7].cpu().numpy(), g['n5_s0_grad_sub'], rtol=5e-4, atol=5e-7)
+    s2 = s.detach().clone().requires_grad_()
+    per = sd.ctc_loss(s2, tg.cuda(), tl.cuda(), reduction='none')
+    clip = float(per.detach().sort().values[1])                      # clips the largest loss only
+    sd.ctc_loss(s2, tg.cuda(), tl.cuda(), loss_clip=clip).backward()
+    worst = int(per.detach().argmax())
+    assert s2.grad[:, worst].abs().max().item() == 0.0
+    assert s2.grad.abs().max().item() > 0.0
+
+
+
 def test_read_set_pipeline_matches_basecall(model5):
     """Device-side chunking + stitching of a whole read set gives exactly the strings of the reference-shaped
     basecall() iterator (short, exact-multiple, stub and multi-chunk reads; ragged last batch)."""

@@ -23,7 +23,7 @@ SYMBOLS = (
     'xb_load_lstm_weights', 'xb_load_head_weights', 'xb_conv_stem_fwd',
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
-    'xb_ctc_crf_loss_fwd', 'xb_stitch', 'xb_gather_chunks', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+    'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
@@ -64,6 +64,7 @@ def load():
     lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
+    lib.xb_ctc_crf_loss_bwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp, vp, vp]
     lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
     lib.xb_gather_chunks.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp]
     lib.xb_compute_scores_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
@@ -300,6 +301,20 @@ class Handle:
         self._check(self.lib.xb_ctc_crf_loss_fwd(self.h, _ptr(s), T, N, _ptr(tg), tg.shape[1], _ptr(ln),
                                                  int(normalise), _ptr(out), _stream(self.device)), 'xb_ctc_crf_loss_fwd')
         return out
+
+    def ctc_loss_bwd(self, scores, targets, lengths, grad_loss, normalise=True):
+        """d(sum_n grad_loss[n] * loss[n]) / d scores, (T, N, C*NZ) fp32."""
+        s, T, N = self._scores(scores)
+        tg = targets.to(self.device, torch.int32).contiguous()
+        ln = lengths.to(self.device, torch.int32).contiguous()
+        gl = grad_loss.to(self.device, torch.float32).contiguous()
+        npos = tg.shape[1] - (self.state_len - 1)
+        ws = torch.empty((T + 1) * N * max(npos, 1), dtype=torch.float32, device=self.device)
+        grad = torch.empty_like(s)
+        self._check(self.lib.xb_ctc_crf_loss_bwd(self.h, _ptr(s), T, N, _ptr(tg), tg.shape[1], _ptr(ln), int(normalise),
+                                                 _ptr(gl), _ptr(ws), _ptr(grad), _stream(self.device)),
+                    'xb_ctc_crf_loss_bwd')
+        return grad
 
     def stitch(self, rows, chunk_first, chunk_count, read_len, chunksize, overlap, stride=5, out_stride=None):
         rows = rows.to(self.device, torch.int8).contiguous()

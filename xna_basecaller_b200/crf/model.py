@@ -33,6 +33,23 @@ def get_stride(m):
     return 1
 
 
+class _CTCLoss(torch.autograd.Function):
+    """Per-sequence CTC-CRF loss with its gradient w.r.t. the scores (xb_ctc_crf_loss_fwd / _bwd), so that
+    `loss.backward()` of the reference's training step (training.py:100-108) reaches the score tensor."""
+
+    @staticmethod
+    def forward(ctx, scores, handle, targets, lengths, normalise):
+        ctx.handle, ctx.normalise = handle, normalise
+        ctx.save_for_backward(scores, targets, lengths)
+        return handle.ctc_loss(scores, targets, lengths, normalise=normalise)
+
+    @staticmethod
+    def backward(ctx, grad):
+        scores, targets, lengths = ctx.saved_tensors
+        g = ctx.handle.ctc_loss_bwd(scores, targets, lengths, grad, normalise=ctx.normalise)
+        return g.to(scores.dtype), None, None, None, None
+
+
 class CTC_CRF:
     """Transition lattice over n_base^state_len states with n_base+1 edges into every state: edge 0 stays
     (blank), edge 1+j arrives from the state whose leading base j was dropped."""
@@ -97,7 +114,7 @@ class CTC_CRF:
         return self._handle(scores).decode(scores)
 
     def ctc_loss(self, scores, targets, target_lengths, loss_clip=None, reduction='mean', normalise_scores=True):
-        loss = self._handle(scores).ctc_loss(scores, targets, target_lengths, normalise=normalise_scores)
+        loss = _CTCLoss.apply(scores, self._handle(scores), targets, target_lengths, normalise_scores)
         if loss_clip:
             loss = torch.clamp(loss, 0.0, loss_clip)
         if reduction == 'mean':

@@ -123,6 +123,91 @@ __global__ void ctc_simple_kernel(const float *__restrict__ scores, int T, int N
     }
 }
 
+// Gradient of the per-sequence loss w.r.t. the scores (what autograd gives the reference through seqdist's Logspace
+// backward, crf/model.py:118-131):  d loss_n / d scores[t,n,e] = (P_den[t,n,e] - P_num[t,n,e]) / len_n, where P_den are
+// the edge posteriors of the full lattice (present only because normalise subtracts logZ/T from every score; the caller
+// has put them into `grad`) and P_num the posteriors of the target's stay / move edges under the alignment lattice.
+// Forward pass stores alpha (T+1, N, npos), the backward pass walks beta and scatters through a shared-memory row.
+__global__ void ctc_simple_bwd_kernel(const float *__restrict__ scores, int T, int N, int S, const int32_t *__restrict__ targets,
+                                      int Lmax, const int32_t *__restrict__ lengths, const float *__restrict__ logz,
+                                      int normalise, int n_base, int state_len, const float *__restrict__ grad_loss,
+                                      float *__restrict__ alpha_ws, float *__restrict__ grad) {
+    extern __shared__ __align__(16) float sm[];
+    const int NT = blockDim.x, j = threadIdx.x, n = blockIdx.x;
+    float *a = sm;                                   // 2 * NT (alpha, then beta)
+    int *mv = reinterpret_cast<int *>(sm + 2 * NT);  // NT + 1: move edge entering position j
+    float *acc = sm + 3 * NT + 1;                    // S
+    float *rowbuf = acc + S;                         // S
+    const int npos = Lmax - (state_len - 1);
+    const int NZ = n_base + 1;
+    const int32_t *tg = targets + (size_t)n * Lmax;
+    const bool act = j < npos;
+    int stay_idx = 0, move_in = 0;
+    if (act) {
+        int st = 0;
+        for (int i = 0; i < state_len; i++) st = st * n_base + max(tg[j + i] - 1, 0);
+        stay_idx = st * NZ;
+        if (j > 0) move_in = stay_idx + max(tg[j - 1] - 1, 0) + 1;
+    }
+    mv[j] = move_in;
+    if (j == 0) mv[NT] = 0;
+    const float shift = normalise ? logz[n] / (float)T : 0.0f;
+    const float *base = scores + (size_t)n * S;
+    const size_t row = (size_t)N * S, arow = (size_t)N * npos;
+    float *aw = alpha_ws + (size_t)n * npos;
+    a[j] = (j == 0) ? 0.0f : XB_NEG_BIG;
+    if (act) aw[j] = a[j];
+    __syncthreads();
+    for (int t = 0; t < T; t++) {
+        for (int i = j; i < S; i += NT) rowbuf[i] = base[(size_t)t * row + i];
+        __syncthreads();
+        const float *ac = a + (t & 1) * NT;
+        float *an = a + ((t + 1) & 1) * NT;
+        float v = XB_NEG_BIG;
+        if (act) {
+            v = XB_ADD(XB_SUB(rowbuf[stay_idx], shift), ac[j]);
+            if (j > 0) v = logaddexp_exact(v, XB_ADD(XB_SUB(rowbuf[move_in], shift), ac[j - 1]));
+            aw[(size_t)(t + 1) * arow + j] = v;
+        }
+        an[j] = v;
+        __syncthreads();
+    }
+    const int len = lengths[n];
+    const int last = len + 1 - state_len - 1;
+    const bool feasible = last >= 0 && last < npos && a[(T & 1) * NT + last] > -1e37f;
+    const float lz = feasible ? a[(T & 1) * NT + last] : 0.0f;
+    const float scale = grad_loss[n] / (float)len;
+    __syncthreads();
+    a[j] = (j == last) ? 0.0f : XB_NEG_BIG;           // beta_T in buffer 0
+    for (int i = 0; i < T; i++) {
+        const int t = T - 1 - i;
+        for (int e = j; e < S; e += NT) { rowbuf[e] = base[(size_t)t * row + e]; acc[e] = 0.0f; }
+        __syncthreads();
+        const float *b1 = a + (i & 1) * NT;
+        float *b0 = a + ((i + 1) & 1) * NT;
+        float bnew = XB_NEG_BIG;
+        if (act) {
+            const float at = aw[(size_t)t * arow + j];
+            const float stay_term = XB_ADD(XB_SUB(rowbuf[stay_idx], shift), b1[j]);
+            if (feasible) {
+                atomicAdd(&acc[stay_idx], xb_expf(XB_SUB(XB_ADD(at, stay_term), lz)));
+                if (j > 0) {
+                    const float am1 = aw[(size_t)t * arow + j - 1];
+                    const float mterm = XB_ADD(XB_SUB(rowbuf[move_in], shift), b1[j]);
+                    atomicAdd(&acc[move_in], xb_expf(XB_SUB(XB_ADD(am1, mterm), lz)));
+                }
+            }
+            bnew = stay_term;
+            if (j + 1 < npos) bnew = logaddexp_exact(bnew, XB_ADD(XB_SUB(rowbuf[mv[j + 1]], shift), b1[j + 1]));
+        }
+        b0[j] = bnew;
+        __syncthreads();
+        float *g = grad + ((size_t)t * N + n) * S;
+        for (int e = j; e < S; e += NT) g[e] = scale * ((normalise ? g[e] : 0.0f) - acc[e]);
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
@@ -164,6 +249,23 @@ int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int3
     size_t smem = sizeof(float) * (2 * NT + 2 * S);
     ctc_simple_kernel<<<N, NT, smem, s>>>(scores, T, N, S, targets, Lmax, lengths, h->logz, normalise, h->n_base,
                                          h->state_len, loss);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+// grad (T, N, S) must hold the Log posteriors of `scores` on entry when normalise != 0 (xb_ctc_crf_loss_bwd puts them there).
+int xb_ctc_loss_bwd_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                         const int32_t *lengths, int normalise, const float *grad_loss, float *alpha_ws, float *grad,
+                         cudaStream_t s) {
+    const int npos = Lmax - (h->state_len - 1);
+    XB_REQUIRE(h, npos >= 1 && npos <= 1024, "Lmax=%d unsupported (1 <= Lmax-state_len+1 <= 1024)", Lmax);
+    const int NT = ((npos + 31) / 32) * 32;
+    const int S = h->C * h->NZ;
+    size_t smem = sizeof(float) * (3 * NT + 1 + 2 * S);
+    if (smem > 48 * 1024)
+        XB_CUDA(h, cudaFuncSetAttribute(ctc_simple_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_simple_bwd_kernel<<<N, NT, smem, s>>>(scores, T, N, S, targets, Lmax, lengths, h->logz, normalise, h->n_base,
+                                             h->state_len, grad_loss, alpha_ws, grad);
     XB_LAUNCH_CHECK(h);
     return XB_OK;
 }

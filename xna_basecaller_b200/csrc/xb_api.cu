@@ -23,6 +23,9 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
+int xb_ctc_loss_bwd_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                         const int32_t *lengths, int normalise, const float *grad_loss, float *alpha_ws, float *grad,
+                         cudaStream_t s);
 int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
                      const int32_t *lengths, int normalise, float *loss, cudaStream_t s);
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
@@ -473,6 +476,18 @@ int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const i
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, targets && lengths && loss, "NULL buffer");
     return xb_ctc_loss_impl(h, scores, T, N, targets, Lmax, lengths, normalise, loss, s);
+}
+
+int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
+                        const int32_t *lengths, int normalise, const float *grad_loss, float *alpha_ws,
+                        float *grad_scores, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, targets && lengths && grad_loss && alpha_ws && grad_scores, "NULL buffer");
+    if (normalise) {       // logZ (for the shift) and the posteriors of the full lattice, straight into grad_scores
+        if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, h->logz, s)) return rc;
+        if (int rc = xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, grad_scores, nullptr, 0, s)) return rc;
+    }
+    return xb_ctc_loss_bwd_impl(h, scores, T, N, targets, Lmax, lengths, normalise, grad_loss, alpha_ws, grad_scores, s);
 }
 
 int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
