@@ -89,3 +89,41 @@ def reference_config(labels=('N', 'A', 'C', 'G', 'T', 'X'), state_len=3):
                     'scale': 5.0, 'rnn_type': 'lstm', 'blank_score': 2.0},
         'basecaller': {'batchsize': 384, 'chunksize': 3600, 'overlap': 500},
     }
+
+
+def install_io():
+    """Also load bonito.io and bonito.fast5 (golden fixtures for the output formats and the signal pre-processing):
+    mappy / pysam / ont_fast5_api are stubbed -- only the pure-Python / numpy functions of those modules are used
+    (write_fastq, summary_row, CSVLogger, Writer in 'wfq' mode; trim, med_mad, norm_by_noisiest_section)."""
+    mods = install()
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Anything:
+        def __init__(self, *a, **k):
+            pass
+
+        @classmethod
+        def from_references(cls, *a, **k):
+            return cls()
+
+    if 'mappy' not in sys.modules:
+        module('mappy', __version__='0.0-stub')
+    if 'pysam' not in sys.modules:
+        module('pysam', AlignmentFile=_Anything, AlignmentHeader=_Anything, AlignedSegment=_Anything)
+    if 'ont_fast5_api' not in sys.modules:
+        pkg = module('ont_fast5_api')
+        pkg.__path__ = []
+        module('ont_fast5_api.fast5_interface', get_fast5_file=None)
+    if 'bonito.cli' not in sys.modules:
+        cli = module('bonito.cli')
+        cli.__path__ = []
+        module('bonito.cli.convert', typical_indices=None)
+    sys.modules['bonito'].__version__ = '0.0-shim'
+    for name in ('bonito.io', 'bonito.fast5'):
+        mods[name] = importlib.import_module(name)
+    return mods

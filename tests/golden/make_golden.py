@@ -65,12 +65,71 @@ def make_crf_grad(RM):
     print('crf_grad.npz', os.path.getsize(os.path.join(OUT, 'crf_grad.npz')))
 
 
+class FakeRead:
+    """The attributes of bonito.fast5.Read that Writer / summary_row touch (fast5.py:22-128)."""
+
+    def __init__(self, i, n):
+        self.read_id, self.filename, self.run_id = 'read-%04d' % i, 'batch_%d.fast5' % (i // 2), 'run%02d' % (i % 3)
+        self.channel, self.mux, self.read_number = 100 + i, 1 + i % 4, 7 * i
+        self.start, self.duration = 1.5 * i, 2.25 + i
+        self.template_start, self.template_duration = self.start + 0.01, self.duration - 0.01
+        self.start_time = '2021-03-0%dT10:00:0%d' % (1 + i % 9, i % 10)
+        self.signal = np.zeros(n, dtype=np.float32)
+
+    def tagdata(self):
+        return ['mx:i:%s' % self.mux, 'ch:i:%s' % self.channel, 'st:Z:%s' % self.start_time, 'rn:i:%s' % self.read_number,
+                'f5:Z:%s' % self.filename]
+
+
+def fake_results():
+    rs = np.random.RandomState(5)
+    out = []
+    for i, n in enumerate((1200, 0, 4000, 333)):
+        seq = ''.join(rs.choice(list('ACGTX'), size=n // 10))
+        out.append((FakeRead(i, n), {'sequence': seq, 'qstring': 'O' * len(seq), 'sig_move': np.zeros(n, dtype=bool)}))
+    return out
+
+
+def make_io():
+    """FASTQ text + summary table written by the reference's own Writer thread (mode 'wfq') for four fake reads."""
+    import io as pyio
+    import json
+    import tempfile
+    mods = refshim.install_io()
+    RIO = mods['bonito.io']
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            fd = pyio.StringIO()
+            RIO.summary_file = lambda: os.path.join(tmp, 'summary.tsv')     # location only; the format is the reference's
+            w = RIO.Writer('wfq', iter(fake_results()), aligner=None, fd=fd, groups=[], group_key='sup_v3.3')
+            w.start(); w.join()
+            summary = open([f for f in os.listdir(tmp) if f.endswith('summary.tsv')][0]).read()
+        finally:
+            os.chdir(cwd)
+    buf = pyio.StringIO()
+    RIO.write_fasta('r1 extra', 'ACGTX', fd=buf)
+    RIO.write_fastq('r2', 'ACX', 'OOO', fd=buf)
+    RU = mods['bonito.util']
+    out = {'fastq': fd.getvalue(), 'summary': summary, 'log': w.log, 'records': buf.getvalue(),
+           'qscores': {q: float(RU.mean_qscore_from_qstring(q)) for q in ('OOOO', '!5I', '+', 'IIIIIIIIII5')},
+           'row_unaligned': {k: (v if isinstance(v, (str, int, float)) else float(v))
+                             for k, v in RIO.summary_row(FakeRead(3, 10), 17, 12.5, alignment=None).items()}}
+    with open(os.path.join(OUT, 'io.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+    print('io.json', os.path.getsize(os.path.join(OUT, 'io.json')))
+
+
 def main():
+    if '--only-io' in sys.argv:
+        return make_io()
     mods = refshim.install()
     RM, RU, RB = mods['bonito.crf.model'], mods['bonito.util'], mods['bonito.crf.basecall']
     if '--only-crf-grad' in sys.argv:
         return make_crf_grad(RM)
     make_crf_grad(RM)
+    make_io()
 
     # ---- (i)+(ii) CRF: reference CTC_CRF methods on synthetic scores
     crf = {}
