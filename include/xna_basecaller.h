@@ -153,6 +153,16 @@ int xb_gather_chunks(xb_handle *h, const void *signal, int sig_dtype, const int6
                      const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
                      int L, float *out, void *stream);
 
+/* Per-read signal pre-processing (the reference's Read.__init__, fast5.py:88-100: DAC -> pA scaling, trim :149-172, then
+ * med/MAD normalisation, or norm_by_noisiest_section for reads of <= 8000 samples after trimming).  raw: concatenated int16
+ * DAC samples, read r = [read_offset[r], read_offset[r] + read_len[r]); scaling[r] = range / digitisation, offset[r] the
+ * channel offset.  out: float32 with the same layout -- the trimmed, normalised signal of read r starts at
+ * out[read_offset[r]] and has out_len[r] samples (feed out / read_offset / out_len to xb_gather_chunks).  stats
+ * (n_reads, 4) float32: trim start, med, mad, mode (0 whole read, 1 noisiest section, 2 nothing left). */
+int xb_preprocess_reads(xb_handle *h, const int16_t *raw, const int64_t *read_offset, const int32_t *read_len,
+                        const double *scaling, const int32_t *offset, int n_reads, float *out, int32_t *out_len,
+                        float *stats, void *stream);
+
 /* crf.basecall.compute_scores end to end with HOST buffers (crf/basecall.py:27-82): H2D of the
  * chunk batch, encoder, decode, D2H of the packed sequences; synchronises.  signal_host (N, L) fp32,
  * seq_host (N, T) int8, lens_host (N).  Pinned host memory makes the copies asynchronous. */

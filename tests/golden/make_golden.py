@@ -65,6 +65,48 @@ def make_crf_grad(RM):
     print('crf_grad.npz', os.path.getsize(os.path.join(OUT, 'crf_grad.npz')))
 
 
+def synthetic_raw_read(seed, n, stall=True):
+    """int16 DAC samples with the features the pre-processing reacts to: k-mer-like level steps, an open-pore stall at
+    the start (what trim() removes) and a quiet stretch (what norm_by_noisiest_section avoids)."""
+    rs = np.random.RandomState(seed)
+    x = 400 + 60 * rs.randn() + 35 * rs.randn(n) + np.repeat(rs.randn(n // 8 + 1) * 25, 8)[:n]
+    if stall:
+        k = min(rs.randint(100, 1500), n)
+        x[:k] += 250 + 30 * rs.randn(k)
+    if n > 3000:
+        q = rs.randint(n // 3, n // 2)
+        x[q:q + rs.randint(200, 900)] *= 0.2
+    return np.clip(np.round(x), -2000, 2000).astype(np.int16)
+
+
+RAW_LENGTHS = (12000, 9000, 8700, 8011, 7000, 4000, 2500, 1000, 450, 150, 99, 30, 12, 15001)
+RAW_SCALING = 1437.976 / 8192
+
+
+def make_preprocess():
+    """The reference's own Read.__init__ arithmetic (fast5.py:88-100) on synthetic raw reads."""
+    import warnings
+    F5 = refshim.install_io()['bonito.fast5']
+    out = {}
+    for i, n in enumerate(RAW_LENGTHS):
+        raw, offset = synthetic_raw_read(1000 + i, n, stall=i % 3 != 2), -240 + i
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            scaled = np.array(np.float64(RAW_SCALING) * (raw + offset), dtype=np.float32)
+            trim_start, _ = F5.trim(scaled[:8000])
+            scaled = scaled[trim_start:]
+            if len(scaled) > 8000:
+                med, mad = F5.med_mad(scaled)
+                signal = (scaled - med) / mad
+            else:
+                signal = F5.norm_by_noisiest_section(scaled)
+        out['r%d_trim' % i] = np.array(trim_start)
+        out['r%d_signal' % i] = signal.astype(np.float32)
+        assert signal.dtype == np.float32
+    np.savez_compressed(os.path.join(OUT, 'preprocess.npz'), **out)
+    print('preprocess.npz', os.path.getsize(os.path.join(OUT, 'preprocess.npz')))
+
+
 class FakeRead:
     """The attributes of bonito.fast5.Read that Writer / summary_row touch (fast5.py:22-128)."""
 
@@ -124,12 +166,15 @@ def make_io():
 def main():
     if '--only-io' in sys.argv:
         return make_io()
+    if '--only-preprocess' in sys.argv:
+        return make_preprocess()
     mods = refshim.install()
     RM, RU, RB = mods['bonito.crf.model'], mods['bonito.util'], mods['bonito.crf.basecall']
     if '--only-crf-grad' in sys.argv:
         return make_crf_grad(RM)
     make_crf_grad(RM)
     make_io()
+    make_preprocess()
 
     # ---- (i)+(ii) CRF: reference CTC_CRF methods on synthetic scores
     crf = {}

@@ -23,7 +23,7 @@ SYMBOLS = (
     'xb_load_lstm_weights', 'xb_load_head_weights', 'xb_conv_stem_fwd',
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
-    'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+    'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
@@ -64,6 +64,7 @@ def load():
     lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
+    lib.xb_preprocess_reads.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_bwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp, vp, vp]
     lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
     lib.xb_gather_chunks.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp]
@@ -340,6 +341,23 @@ class Handle:
         self._check(self.lib.xb_gather_chunks(self.h, _ptr(signal), code, _ptr(read_offset), _ptr(read_len), _ptr(chunk_read),
                                               _ptr(chunk_start), n, L, _ptr(out), _stream(self.device)), 'xb_gather_chunks')
         return out
+
+    def preprocess(self, raw, read_offset, read_len, scaling, offset):
+        """Raw int16 reads (concatenated) -> (normalised float32 signal in the same layout, out_len (n) int32,
+        stats (n, 4) float32 = trim start, med, mad, mode).  fast5.py:88-100 on the GPU."""
+        dev = self.device
+        raw = raw.to(dev, torch.int16).contiguous()
+        ro = torch.as_tensor(read_offset, dtype=torch.int64, device=dev).contiguous()
+        rl = torch.as_tensor(read_len, dtype=torch.int32, device=dev).contiguous()
+        sc = torch.as_tensor(scaling, dtype=torch.float64, device=dev).contiguous()
+        of = torch.as_tensor(offset, dtype=torch.int32, device=dev).contiguous()
+        n = ro.numel()
+        out = torch.empty(raw.numel(), dtype=torch.float32, device=dev)
+        out_len = torch.empty(n, dtype=torch.int32, device=dev)
+        stats = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        self._check(self.lib.xb_preprocess_reads(self.h, _ptr(raw), _ptr(ro), _ptr(rl), _ptr(sc), _ptr(of), n, _ptr(out),
+                                                 _ptr(out_len), _ptr(stats), _stream(dev)), 'xb_preprocess_reads')
+        return out, out_len, stats
 
     def compute_scores_host(self, signal_host, seq_host=None, lens_host=None):
         """signal_host: (N, L) fp32 CPU tensor (pinned for async copies) -> packed sequences on the host."""

@@ -23,6 +23,9 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
+int xb_preprocess_impl(xb_handle *h, const int16_t *raw, const int64_t *read_offset, const int32_t *read_len,
+                       const double *scaling, const int32_t *offset, int n_reads, float *out, int32_t *out_len,
+                       float *stats, cudaStream_t s);
 int xb_ctc_loss_bwd_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
                          const int32_t *lengths, int normalise, const float *grad_loss, float *alpha_ws, float *grad,
                          cudaStream_t s);
@@ -507,6 +510,16 @@ int xb_gather_chunks(xb_handle *h, const void *signal, int sig_dtype, const int6
     XB_CUDA(h, cudaSetDevice(h->device));
     return xb_gather_chunks_impl(h, signal, sig_dtype, read_offset, read_len, chunk_read, chunk_start, n_chunks, L, out,
                                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+int xb_preprocess_reads(xb_handle *h, const int16_t *raw, const int64_t *read_offset, const int32_t *read_len,
+                        const double *scaling, const int32_t *offset, int n_reads, float *out, int32_t *out_len,
+                        float *stats, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, raw && read_offset && read_len && scaling && offset && out && out_len && stats, "NULL buffer");
+    XB_CUDA(h, cudaSetDevice(h->device));
+    return xb_preprocess_impl(h, raw, read_offset, read_len, scaling, offset, n_reads, out, out_len, stats,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L, int8_t *seq_host, int32_t *lens_host,

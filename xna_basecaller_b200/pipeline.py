@@ -82,7 +82,10 @@ class ReadSetBasecaller:
             self._pinned[dtype] = buf
         return buf[:n]
 
-    def basecall(self, signals):
+    def basecall(self, signals, scaling=None, offset=None):
+        """signals: normalised reads (float32, or int16 already in model units) -- or, with scaling / offset given (one per
+        read: channel range / digitisation and channel offset, fast5.py:66,64), RAW int16 DAC reads, which are scaled,
+        trimmed and med/MAD-normalised on the GPU first (xb_preprocess_reads = the reference's Read.__init__)."""
         import time
         dev, cs, ov, T = self.device, self.chunksize, self.overlap, self.chunksize // self.stride
         n_reads = len(signals)
@@ -90,21 +93,31 @@ class ReadSetBasecaller:
             return [], {'reads': 0, 'samples': 0, 'chunks': 0, 'seconds': 0.0, 'seconds_stage_h2d': 0.0,
                         'seconds_gpu_batches': 0.0, 'seconds_stitch_d2h': 0.0, 'seconds_strings': 0.0}
         lengths = np.fromiter((len(s) for s in signals), dtype=np.int64, count=n_reads)
-        plan = plan_chunks(lengths, cs, ov)
-        n_chunks = len(plan['chunk_read'])
+        raw_lengths = lengths
         offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
         dtype = torch.int16 if signals[0].dtype == np.int16 else torch.float32
+        if scaling is not None and dtype != torch.int16:
+            raise ValueError('raw reads (scaling / offset given) must be int16 DAC samples')
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         host = self._staging(int(lengths.sum()), dtype)
         np.concatenate(signals, out=host.numpy())          # one pass into pinned memory, then a single H2D
         sig = host.to(dev, non_blocking=True)
+        eng = self.model.seqdist.engine
+        if scaling is not None:
+            h0 = eng.get(dev, self.batchsize, T, bf16=next(self.model.parameters()).dtype == torch.bfloat16)
+            sig, out_len, _ = h0.preprocess(sig, offsets, lengths, np.asarray(scaling, dtype=np.float64),
+                                            np.asarray(offset, dtype=np.int32))
+            lengths = out_len.cpu().numpy().astype(np.int64)       # trimmed lengths decide the chunk table
+            if int(lengths.min()) <= 0:
+                raise ValueError('read %d has no samples left after trimming' % int(lengths.argmin()))
+        plan = plan_chunks(lengths, cs, ov)
+        n_chunks = len(plan['chunk_read'])
         as_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
         read_offset, read_len = as_dev(offsets, torch.int64), as_dev(lengths, torch.int32)
         chunk_read, chunk_start = as_dev(plan['chunk_read'], torch.int32), as_dev(plan['chunk_start'], torch.int32)
 
         t1 = time.perf_counter()
-        eng = self.model.seqdist.engine
         h = eng.get(dev, min(self.batchsize, n_chunks), T, bf16=next(self.model.parameters()).dtype == torch.bfloat16)
         self.model.encoder.sync_weights(h)
         rows = torch.empty(n_chunks, T, dtype=torch.int8, device=dev)
@@ -123,7 +136,7 @@ class ReadSetBasecaller:
         seconds = time.perf_counter() - t0
         flat = out_host.view('u1')
         strings = [flat[i, :len_host[i]].tobytes().decode('ascii') for i in range(n_reads)]
-        return strings, {'reads': n_reads, 'samples': int(lengths.sum()), 'chunks': n_chunks, 'seconds': seconds,
+        return strings, {'reads': n_reads, 'samples': int(raw_lengths.sum()), 'chunks': n_chunks, 'seconds': seconds,
                          'seconds_stage_h2d': t1 - t0, 'seconds_gpu_batches': t2 - t1, 'seconds_stitch_d2h': seconds - (t2 - t0),
                          'seconds_strings': time.perf_counter() - t0 - seconds}
 
