@@ -17,6 +17,7 @@
 #include "xb_common.cuh"
 #include "xb_ptx.cuh"
 #include "xb_gemm.cuh"
+#include "xb_head_epilogue.cuh"
 
 using namespace xbptx;
 
@@ -30,35 +31,6 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*b
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-
-// LinearCRFEncoder epilogue for 32 consecutive head columns whose first column sits at position E0 inside its group
-// of NB: scale*tanh(acc + bias), blank score in front of every group.  NB and E0 are compile-time, so every staged
-// position is an immediate offset (the generic loop spends more instructions on index bookkeeping than on the tanh).
-// Sg points at the staged position of the blank of the group that holds column 0.
-template <int NB, int E0>
-__device__ __forceinline__ void head_expand32(const uint32_t (&acc)[32], const float *__restrict__ bias, float scale, float blank,
-                                              float *Sg) {
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        constexpr int dummy = 0; (void)dummy;
-        const int g = (E0 + j) / NB, e = (E0 + j) % NB;
-        const float v = scale * fast_tanh(__uint_as_float(acc[j]) + __ldg(bias + j));
-        if (e == 0) Sg[g * (NB + 1)] = blank;
-        Sg[g * (NB + 1) + 1 + e] = v;
-    }
-}
-template <int NB>
-__device__ __forceinline__ void head_expand32_nb(int e0, const uint32_t (&acc)[32], const float *__restrict__ bias, float scale,
-                                                 float blank, float *Sg) {
-    switch (e0) {
-        case 0: head_expand32<NB, 0>(acc, bias, scale, blank, Sg); break;
-        case 1: head_expand32<NB, 1 % NB>(acc, bias, scale, blank, Sg); break;
-        case 2: head_expand32<NB, 2 % NB>(acc, bias, scale, blank, Sg); break;
-        case 3: head_expand32<NB, 3 % NB>(acc, bias, scale, blank, Sg); break;
-        case 4: head_expand32<NB, 4 % NB>(acc, bias, scale, blank, Sg); break;
-        default: head_expand32<NB, 5 % NB>(acc, bias, scale, blank, Sg); break;
-    }
-}
 
 template <bool BF16, int EPI>
 __global__ void __launch_bounds__(256, EPI == EPI_LSTM ? 1 : 2)
@@ -267,48 +239,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {   // EPI_HEAD
                 constexpr int RS = 81;                           // staged row pitch in floats (odd: conflict free)
                 float *S = reinterpret_cast<float *>(stg);
-                const int nbs = p.n_base;
                 const int col0 = n0 + c0;                        // head columns of this warp: [col0, col_end)
                 const int col_end = min(col0 + HN, p.head_rows);
-                int seg_start = 0, seg_len = 0;
-                if (col_end > col0) {
-                    if (p.expand) {
-                        seg_start = col0 + col0 / nbs + ((col0 % nbs) ? 1 : 0);
-                        seg_len = (col_end - 1) + (col_end - 1) / nbs + 2 - seg_start;
-                    } else {
-                        seg_start = col0;
-                        seg_len = col_end - col0;
-                    }
-                }
+                int seg_start, seg_len;
+                xbhead::segment(col0, col_end, p.n_base, p.expand, seg_start, seg_len);
 #pragma unroll 1
                 for (int cb = c0; cb < c0 + HN; cb += 32) {
                     if (n0 + cb >= col_end) break;
                     uint32_t acc[32];
                     tmem_ld_32x32b_x32(taddr + cb, acc);
                     tmem_ld_wait();
-                    int col = n0 + cb, c = col / nbs, e = col - c * nbs;
-                    float *Sr = S + lane * RS;
-                    if (p.expand && col + 32 <= col_end && nbs >= 4 && nbs <= 6) {      // all 32 columns valid: static path
-                        float *Sg = Sr + c * (nbs + 1) - seg_start;
-                        if (nbs == 5) head_expand32_nb<5>(e, acc, p.bias + col, p.scale, p.blank, Sg);
-                        else if (nbs == 4) head_expand32_nb<4>(e, acc, p.bias + col, p.scale, p.blank, Sg);
-                        else head_expand32_nb<6>(e, acc, p.bias + col, p.scale, p.blank, Sg);
-                        continue;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j++, col++) {
-                        if (col < col_end) {
-                            const float v = p.scale * fast_tanh(__uint_as_float(acc[j]) + __ldg(p.bias + col));
-                            if (p.expand) {
-                                const int o = col + c + 1 - seg_start;
-                                if (e == 0) Sr[o - 1] = p.blank;
-                                Sr[o] = v;
-                                if (++e == nbs) { e = 0; c++; }
-                            } else {
-                                Sr[col - seg_start] = v;
-                            }
-                        }
-                    }
+                    xbhead::stage32(acc, n0 + cb, col_end, p.n_base, p.expand, p.bias, p.scale, p.blank, S + lane * RS, seg_start);
                 }
                 __syncwarp();
                 float *obase = reinterpret_cast<float *>(p.out) + seg_start;

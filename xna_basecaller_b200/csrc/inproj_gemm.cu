@@ -22,6 +22,7 @@
 #include "xb_common.cuh"
 #include "xb_ptx.cuh"
 #include "xb_gemm.cuh"
+#include "xb_head_epilogue.cuh"
 
 using namespace xbptx;
 
@@ -29,35 +30,77 @@ namespace {
 
 constexpr int BM = 128, BNI = 64, BK = 64;
 constexpr int KB = XB_FEATURES / BK;                 // 12 K blocks
-constexpr int NT = XB_GATES / BNI;                   // 48 N tiles
+constexpr int MAX_COLS = XB_GATES;                   // most output columns (rows of W) a launch handles: 48 N tiles
 constexpr int KPS = 4;                               // K blocks per pipeline stage (one 3-D TMA box, 16 MMAs per wait)
 constexpr int SPT = KB / KPS;                        // stages per N tile
-constexpr int STAGES = 6;
+enum { IP_GATES = 0, IP_SCORES = 1 };                // epilogue: 16-bit gates (+bias) | fp32 CRF scores (LinearCRFEncoder)
+template <int EPI> struct IPCfg {
+    static constexpr int STAGES = EPI == IP_GATES ? 6 : 4;
+    static constexpr int SETS = EPI == IP_GATES ? 1 : 2;     // epilogue warp sets (4 warps each) taking alternate accumulators
+    static constexpr int THREADS = (4 + 4 * SETS) * 32;
+    static constexpr int STG_BYTES = EPI == IP_GATES ? 32 * (BNI * 2 + 16) : 32 * 81 * 4;     // per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * (KPS * BNI * BK * 2) + 4 * SETS * STG_BYTES + MAX_COLS * 4 + 1024 /*align*/ + 512 /*barriers*/;
+};
 constexpr int KBLOCK_BYTES = BNI * BK * 2;           // 8 KB: one [64 rows x 128 B] swizzle atom column
 constexpr int STAGE_BYTES = KPS * KBLOCK_BYTES;      // 32 KB
 constexpr int A_COLS = XB_FEATURES / 2;              // 384 TMEM columns hold the x block
 constexpr int ROW_PITCH = BNI * 2 + 16;              // staged epilogue row pitch (bytes)
-constexpr int STG_BYTES = 32 * ROW_PITCH;            // per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + XB_GATES * 4 + 1024 /*align*/ + 512 /*barriers*/;
 
 struct IPParams {
     const uint16_t *x;        // (M, 768) 16-bit
-    const float *bias;        // (3072) fp32, same column order as the rows of W_ih
-    uint16_t *out;            // (M, 3072) 16-bit
+    const float *bias;        // (n_valid) fp32, same column order as the rows of W
+    void *out;                // IP_GATES: (M, ldo) 16-bit; IP_SCORES: (M, ldo) fp32
     int M;
+    int NT;                   // N tiles of 64 columns (rows of W, zero padded to a multiple of 64)
+    int n_valid, ldo;         // valid output columns before expansion; output row pitch in elements
+    int n_base, expand;       // IP_SCORES: blank score inserted in front of every n_base columns
+    float scale, blank;
     int no_prefetch;
     long long *dbg;           // optional (XB_INPROJ_DEBUG): stall cycles of the MMA thread of CTA 0: [acc_empty, full, issue, a_ready]
 };
 
-template <bool BF16>
-__global__ void __launch_bounds__(256, 1)
+// LinearCRFEncoder expansion of one thread's 64 activated columns into its staged row (shared address sr, positions
+// relative to the segment start): column jj of the tile goes to pos0 + jj + (e0 + jj) / NB, the blank score in front of
+// every column that starts a group.  NB compile-time (division by a constant), explicit st.shared (through the lambda the
+// compiler had lost the address space and emitted generic stores with 64-bit address arithmetic and a branch per column).
+template <int NB, bool FULL>
+__device__ __forceinline__ void head_stage64(const float (&v)[BNI], uint32_t sr, int e0, int pos0, int ncols, float blank) {
+#pragma unroll
+    for (int jj = 0; jj < BNI; jj++) {
+        if (FULL || jj < ncols) {
+            const unsigned u = (unsigned)(e0 + jj);
+            const unsigned g = u / NB;
+            const uint32_t a = sr + 4u * (uint32_t)(pos0 + jj + (int)g);
+            sts_f32(a, v[jj]);
+            if (u - g * NB == 0) sts_f32(a - 4u, blank);
+        }
+    }
+}
+template <bool FULL>
+__device__ __forceinline__ void head_stage64_dyn(const float (&v)[BNI], uint32_t sr, int nb, int e0, int pos0, int ncols, float blank) {
+    int e = e0, o = pos0;
+#pragma unroll
+    for (int jj = 0; jj < BNI; jj++) {
+        if (FULL || jj < ncols) {
+            if (e == 0) sts_f32(sr + 4u * (uint32_t)(o - 1), blank);
+            sts_f32(sr + 4u * (uint32_t)o, v[jj]);
+            o++;
+            if (++e == nb) { e = 0; o++; }
+        }
+    }
+}
+
+template <bool BF16, int EPI>
+__global__ void __launch_bounds__(IPCfg<EPI>::THREADS, 1)
 inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
     using X = xb16<BF16>;
+    constexpr int STAGES = IPCfg<EPI>::STAGES, STG_BYTES = IPCfg<EPI>::STG_BYTES;
+    const int NT = p.NT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *stgbuf = smem + STAGES * STAGE_BYTES;
-    float *sbias = reinterpret_cast<float *>(stgbuf + 4 * STG_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(sbias + XB_GATES);
+    float *sbias = reinterpret_cast<float *>(stgbuf + 4 * IPCfg<EPI>::SETS * STG_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sbias + MAX_COLS);
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;      // [2]
     uint64_t *acc_empty = acc_full + 2;       // [2]
@@ -84,7 +127,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         tmem_alloc(tmem_holder, 512);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < XB_GATES; i += 256) sbias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < NT * BNI; i += IPCfg<EPI>::THREADS) sbias[i] = i < p.n_valid ? p.bias[i] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -150,9 +193,13 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         if (dbg && lane == 0) { p.dbg[0] = st_acc; p.dbg[1] = st_full; p.dbg[2] = st_issue; p.dbg[3] = st_a; p.dbg[4] = tit; }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ x block loader + epilogue
+        // Scores variant: two sets of four warps; set s runs the epilogues of the accumulators with (N-tile counter & 1) == s,
+        // so consecutive epilogues overlap (each is several times longer than the MMAs of an N tile); set 0 loads the x blocks.
+        constexpr int SETS = IPCfg<EPI>::SETS;
+        const int set = (warp - 4) >> 2;
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint8_t *stg = stgbuf + q * STG_BYTES;
+        uint8_t *stg = stgbuf + (set * 4 + q) * STG_BYTES;
         uint32_t nit = 0;
         bool pending = false;                                  // epilogue of the previous tile's last N tile
         int pend_m0 = 0;
@@ -171,37 +218,110 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);       // the MMAs of N tile ni+2 may overwrite it now
-            const float *bs = sbias + nt * BNI;
-            uint4 *d = reinterpret_cast<uint4 *>(stg + lane * ROW_PITCH);
+            if constexpr (EPI == IP_GATES) {
+                const float *bs = sbias + nt * BNI;
+                uint4 *d = reinterpret_cast<uint4 *>(stg + lane * ROW_PITCH);
+    #pragma unroll
+                for (int j = 0; j < BNI / 8; j++) {
+                    uint32_t pk[4];
+    #pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        pk[e] = X::pack(__uint_as_float(acc[8 * j + 2 * e]) + bs[8 * j + 2 * e],
+                                        __uint_as_float(acc[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1]);
+                    d[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                __syncwarp();
+                const int sub = lane >> 3, l8 = lane & 7;          // 8 lanes x 16 B = one 128-byte row segment
+    #pragma unroll
+                for (int rr = 0; rr < 32; rr += 4) {
+                    const int mm = m0 + q * 32 + rr + sub;
+                    if (mm < p.M)
+                        reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + (size_t)mm * p.ldo + nt * BNI)[l8] =
+                            *reinterpret_cast<const uint4 *>(stg + (rr + sub) * ROW_PITCH + l8 * 16);
+                }
+            } else {
+                // LinearCRFEncoder: scale * tanh(acc + bias), blank score in front of every group of n_base columns; the
+                // thread's row goes to a staged row (odd pitch: conflict free), rows leave as coalesced fp32 segments
+                constexpr int RS = 81;
+                float *S = reinterpret_cast<float *>(stg);
+                const bool dbg = p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0;
+                const long long te0 = clock64();
+                const int col0 = nt * BNI, col_end = min(col0 + BNI, p.n_valid);
+                int seg_start, seg_len;
+                xbhead::segment(col0, col_end, p.n_base, p.expand, seg_start, seg_len);
+                if (seg_len > 0) {
+                    // activation first (64 independent MUFU chains), then the expansion with running positions: no
+                    // compile-time variants per (n_base, group phase) here -- the issue slots are idle anyway, the instruction
+                    // cache is not
+                    const float *bs = sbias + col0;
+                    float v[BNI];
 #pragma unroll
-            for (int j = 0; j < BNI / 8; j++) {
-                uint32_t pk[4];
+                    for (int jj = 0; jj < BNI; jj++) v[jj] = p.scale * xbhead::fast_tanh(__uint_as_float(acc[jj]) + bs[jj]);
+                    const uint32_t sr = smem_u32(S) + (uint32_t)(lane * RS * 4);
+                    const int ncols = col_end - col0;
+                    if (p.expand) {
+                        const int nb = p.n_base, c = col0 / nb, e0 = col0 - c * nb;
+                        const int pos0 = col0 + c + 1 - seg_start;         // staged position of column col0
+                        if (ncols == BNI) {
+                            if (nb == 5) head_stage64<5, true>(v, sr, e0, pos0, ncols, p.blank);
+                            else if (nb == 4) head_stage64<4, true>(v, sr, e0, pos0, ncols, p.blank);
+                            else if (nb == 6) head_stage64<6, true>(v, sr, e0, pos0, ncols, p.blank);
+                            else head_stage64_dyn<true>(v, sr, nb, e0, pos0, ncols, p.blank);
+                        } else {
+                            head_stage64_dyn<false>(v, sr, nb, e0, pos0, ncols, p.blank);
+                        }
+                    } else {
 #pragma unroll
-                for (int e = 0; e < 4; e++)
-                    pk[e] = X::pack(__uint_as_float(acc[8 * j + 2 * e]) + bs[8 * j + 2 * e],
-                                    __uint_as_float(acc[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1]);
-                d[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-            __syncwarp();
-            const int sub = lane >> 3, l8 = lane & 7;          // 8 lanes x 16 B = one 128-byte row segment
+                        for (int jj = 0; jj < BNI; jj++)
+                            if (jj < ncols) sts_f32(sr + 4u * jj, v[jj]);
+                    }
+                    __syncwarp();
+                    if (dbg) p.dbg[6] += clock64() - te0;
+                    // four rows per round, all shared-memory loads before the stores: with only four epilogue warps per SM
+                    // a load -> store chain per row segment leaves the copy-out latency-bound
+                    float *obase = reinterpret_cast<float *>(p.out) + seg_start + lane;
+                    const uint32_t sl = smem_u32(S) + 4u * lane;
+                    const bool k0 = lane < seg_len, k1 = lane + 32 < seg_len, k2 = lane + 64 < seg_len;      // seg_len <= 78
+#pragma unroll 1
+                    for (int rr = 0; rr < 32; rr += 4) {
+                        float w[4][3];
 #pragma unroll
-            for (int rr = 0; rr < 32; rr += 4) {
-                const int mm = m0 + q * 32 + rr + sub;
-                if (mm < p.M)
-                    reinterpret_cast<uint4 *>(p.out + (size_t)mm * XB_GATES + nt * BNI)[l8] =
-                        *reinterpret_cast<const uint4 *>(stg + (rr + sub) * ROW_PITCH + l8 * 16);
+                        for (int r = 0; r < 4; r++) {
+                            const uint32_t a = sl + (uint32_t)((rr + r) * RS * 4);
+                            w[r][0] = k0 ? lds_f32(a) : 0.0f;
+                            w[r][1] = k1 ? lds_f32(a + 128) : 0.0f;
+                            w[r][2] = k2 ? lds_f32(a + 256) : 0.0f;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int mm = m0 + q * 32 + rr + r;
+                            if (mm < p.M) {
+                                float *o = obase + (size_t)mm * p.ldo;
+                                if (k0) o[0] = w[r][0];
+                                if (k1) o[32] = w[r][1];
+                                if (k2) o[64] = w[r][2];
+                            }
+                        }
+                    }
+                    if (dbg) p.dbg[7] += clock64() - te0;
+                }
             }
             __syncwarp();
         };
 
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // One extra (drain) round after the last tile, so that the epilogue lambda has a single call site (it is large
+        // and gets inlined: three copies overflowed the instruction cache in the scores variant).
+        for (int tile = blockIdx.x; tile < ntiles || pending; tile += gridDim.x) {
+            const bool valid = tile < ntiles;
             const int m0 = tile * BM;
-            if (pending) {                                     // all MMAs of the previous tile have completed:
-                mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);   // its x block may be replaced
+            // all MMAs of the previous tile have completed: its x block may be replaced (set 0), its last accumulator read
+            // (the set that owns it; a set never waits on the other set's barrier, it could fall two phases behind)
+            if (pending && (set == 0 || (int)((nit - 1) & 1) == set)) {
+                mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);
                 tc_fence_after();
             }
             const long long tl0 = clock64();
-            {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
+            if (valid && set == 0) {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
                 // during this, so it has to be quick: a direct row-per-thread read costs one L1 wavefront per lane
                 // (12 k wavefronts per tile, ~20 k cycles).  Instead a warp reads its 32 rows coalesced, 128 bytes
                 // (= one K block) of four rows per instruction, four K blocks in flight, transposes through its
@@ -242,28 +362,35 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                 }
             }
             if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) p.dbg[5] += clock64() - tl0;
-            if (pending) epilogue(pend_m0, NT - 1, nit - 1);
-            for (int nt = 0; nt < NT - 1; nt++, nit++) {
-                if (nt == NT - 8 && !p.no_prefetch) {      // next tile's x rows into L2 shortly before they are needed (G streams through L2)
-                    const int mn = m0 + (int)gridDim.x * BM + r;
-                    if (mn < p.M) {
-                        const char *nx = reinterpret_cast<const char *>(p.x + (size_t)mn * XB_FEATURES);
+            // nt = -1: the previous tile's last N tile (its accumulator was awaited above), then N tiles 0 .. NT-2 of this one
+            for (int nt = -1; nt < (valid ? NT - 1 : 0); nt++) {
+                int em0, ent;
+                uint32_t eni;
+                if (nt < 0) {
+                    if (!pending || (SETS > 1 && (int)((nit - 1) & 1) != set)) continue;
+                    em0 = pend_m0; ent = NT - 1; eni = nit - 1;
+                } else {
+                    if (SETS > 1 && (int)(nit & 1) != set) { nit++; continue; }
+                    if (nt == (NT > 8 ? NT - 8 : 0) && !p.no_prefetch) {      // next tile's x rows into L2 shortly before they are needed (G streams through L2)
+                        const int mn = m0 + (int)gridDim.x * BM + r;
+                        if (mn < p.M) {
+                            const char *nx = reinterpret_cast<const char *>(p.x + (size_t)mn * XB_FEATURES);
 #pragma unroll
-                        for (int i = 0; i < 12; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i * 128));
+                            for (int i = 0; i < 12; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i * 128));
+                        }
                     }
+                    mbar_wait(&acc_full[nit & 1], (nit >> 1) & 1);
+                    tc_fence_after();
+                    em0 = m0; ent = nt; eni = nit;
+                    nit++;
                 }
-                mbar_wait(&acc_full[nit & 1], (nit >> 1) & 1);
-                tc_fence_after();
-                epilogue(m0, nt, nit);
+                epilogue(em0, ent, eni);
             }
-            nit++;                                             // the last N tile is finished after the next x load
-            pending = true;
-            pend_m0 = m0;
-        }
-        if (pending) {
-            mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);
-            tc_fence_after();
-            epilogue(pend_m0, NT - 1, nit - 1);
+            if (valid) {
+                nit++;                                         // the last N tile is finished after the next x load
+                pend_m0 = m0;
+            }
+            pending = valid;
         }
     }
     tc_fence_before();
@@ -276,15 +403,11 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
 
 }  // namespace
 
-// gates (M, 3072) 16-bit = x (M, 768) . w_ih^T + bias
-int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s) {
+template <int EPI>
+static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaStream_t s) {
     CUtensorMap tmW;
-    if (int rc = xb_make_tmap_hview(h, &tmW, w_ih, XB_GATES, BNI, KPS)) return rc;
-    IPParams p;
-    p.x = reinterpret_cast<const uint16_t *>(x);
-    p.bias = bias;
-    p.out = reinterpret_cast<uint16_t *>(gates);
-    p.M = M;
+    if (int rc = xb_make_tmap_hview(h, &tmW, w, w_rows, BNI, KPS)) return rc;
+    p.NT = w_rows / BNI;
     p.dbg = nullptr;
     p.no_prefetch = getenv("XB_INPROJ_NOPF") ? 1 : 0;
     if (getenv("XB_INPROJ_DEBUG")) {
@@ -292,30 +415,58 @@ int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float 
         if (!d) cudaMalloc(&d, 64);
         p.dbg = d;
     }
-    const int ntiles = (M + BM - 1) / BM;
+    const int ntiles = (p.M + BM - 1) / BM;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
+    constexpr int SMEM_BYTES = IPCfg<EPI>::SMEM_BYTES;
     static bool configured[2][64] = {};   // per device: function attributes live in the device's context
     const int dv = h->device & 63;
     if (h->bf16) {
         if (!configured[1][dv]) {
-            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             configured[1][dv] = true;
         }
-        inproj_kernel<true><<<grid, 256, SMEM_BYTES, s>>>(tmW, p);
+        inproj_kernel<true, EPI><<<grid, IPCfg<EPI>::THREADS, SMEM_BYTES, s>>>(tmW, p);
     } else {
         if (!configured[0][dv]) {
-            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             configured[0][dv] = true;
         }
-        inproj_kernel<false><<<grid, 256, SMEM_BYTES, s>>>(tmW, p);
+        inproj_kernel<false, EPI><<<grid, IPCfg<EPI>::THREADS, SMEM_BYTES, s>>>(tmW, p);
     }
     XB_LAUNCH_CHECK(h);
     if (p.dbg) {
-        long long v[6];
+        long long v[8];
         cudaDeviceSynchronize();
         cudaMemcpy(v, p.dbg, sizeof v, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "inproj MMA thread of CTA 0: %lld tiles; stall cycles: acc_empty %lld, full %lld, a_ready %lld; issue %lld; x-block load (warp 4) %lld\n", v[4], v[0], v[1], v[3], v[2], v[5]);
+        fprintf(stderr, "inproj MMA thread of CTA 0: %lld tiles; stall cycles: acc_empty %lld, full %lld, a_ready %lld; issue %lld; x-block load (warp 4) %lld; head epilogue stage %lld, stage+copy %lld\n", v[4], v[0], v[1], v[3], v[2], v[5], v[6], v[7]);
         cudaMemset(p.dbg, 0, 64);
     }
     return XB_OK;
+}
+
+// gates (M, 3072) 16-bit = x (M, 768) . w_ih^T + bias
+int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s) {
+    IPParams p = {};
+    p.x = reinterpret_cast<const uint16_t *>(x);
+    p.bias = bias;
+    p.out = gates;
+    p.M = M;
+    p.n_valid = XB_GATES; p.ldo = XB_GATES;
+    return ip_launch<IP_GATES>(h, w_ih, XB_GATES, p, s);
+}
+
+// CRF scores (M, ldo) fp32 = LinearCRFEncoder(x): the same A-stationary kernel with the head epilogue -- a CTA owns whole
+// output rows, W_head (<= 2 MB) streams from L2.  w_rows = rows of the zero-padded weight (multiple of 64, <= 3072).
+int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w_rows, const float *bias, int head_rows,
+                               float *scores, int ldo, int M, cudaStream_t s) {
+    XB_REQUIRE(h, w_rows % BNI == 0 && w_rows <= MAX_COLS && head_rows <= w_rows, "head of %d rows unsupported", head_rows);
+    IPParams p = {};
+    p.x = reinterpret_cast<const uint16_t *>(x);
+    p.bias = bias;
+    p.out = scores;
+    p.M = M;
+    p.n_valid = head_rows; p.ldo = ldo;
+    p.n_base = h->n_base; p.expand = h->expand_blanks;
+    p.scale = h->scale; p.blank = h->blank_score;
+    return ip_launch<IP_SCORES>(h, w, w_rows, p, s);
 }

@@ -23,6 +23,8 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
+int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w_rows, const float *bias, int head_rows,
+                               float *scores, int ldo, int M, cudaStream_t s);
 int xb_preprocess_impl(xb_handle *h, const int16_t *raw, const int64_t *read_offset, const int32_t *read_len,
                        const double *scaling, const int32_t *offset, int n_reads, float *out, int32_t *out_len,
                        float *stats, cudaStream_t s);
@@ -405,6 +407,10 @@ int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     xb_stage_timer tm(h, XB_ST_HEAD, s);
+    static const bool tile_gemm = getenv("XB_HEAD_GENERIC") != nullptr;      // the 128x128 tile GEMM, kept for cross-checks
+    if (!tile_gemm)
+        return xb_head_astationary_launch(h, x_tnc, h->head_w, h->head_rows_padded, h->head_b, h->head_rows, scores,
+                                          h->expand_blanks ? h->C * h->NZ : h->head_rows, T * N, s);
     CUtensorMap tmA, tmB;
     if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
     if (int rc = xb_make_tmap_2d(h, &tmB, h->head_w, h->head_rows_padded, XB_FEATURES, XB_FEATURES)) return rc;

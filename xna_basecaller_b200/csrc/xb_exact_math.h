@@ -108,7 +108,6 @@ XB_HD float xb_logf(float x) {
 //   xb_expf_le0: x <= 0 (a score minus a running maximum), so no overflow branch;
 //   xb_logf_norm: x a positive normal number (a sum of exponentials >= 1, or a posterior + 1e-8).
 XB_HD float xb_expf_le0(float x) {
-    if (!(x >= -86.0f)) return 0.0f;
     const float magic = 12582912.0f;
     float t = XB_FMA(x, 1.44269504088896341f, magic);
     float n = XB_SUB(t, magic);
@@ -123,8 +122,11 @@ XB_HD float xb_expf_le0(float x) {
     p = XB_FMA(p, r, 5.0000001201e-1f);
     p = XB_FMA(p, z, r);
     p = XB_ADD(p, 1.0f);
-    int32_t ni = (int32_t)n;
-    return XB_U2F(XB_F2U(p) + ((uint32_t)ni << 23));
+    // the exponent comes from the integer part of t (= magic + n: its low mantissa bits hold n in two's complement),
+    // and the underflow case is a select at the end instead of an early return: no divergent branch per call
+    uint32_t ni = XB_F2U(t) - 0x4b400000u;
+    float v = XB_U2F(XB_F2U(p) + (ni << 23));
+    return (x >= -86.0f) ? v : 0.0f;
 }
 
 XB_HD float xb_logf_norm(float x) {

@@ -42,6 +42,14 @@ __device__ __forceinline__ void red_release_gpu_add(int *p, int v) {
 __device__ __forceinline__ void red_relaxed_gpu_add(int *p, int v) {
     asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
