@@ -86,3 +86,39 @@ def test_raw_reads_through_the_read_set_pipeline():
     want, _ = caller.basecall([pp.preprocess(r, s, o)[0] for r, s, o in zip(raws, scal, offs)])
     assert got == want and all(len(s) > 0 for s in got)
     assert counters['samples'] == sum(len(r) for r in raws)
+
+
+def test_raw_reads_to_fastq():
+    """Raw reads -> xb_preprocess_reads -> encoder / decode / stitch on the device -> io.Writer: FASTQ records + summary rows."""
+    import io as pyio
+    from oracle import bonito_oracle as bo
+    from test_cpu_host import sup_config
+    from xna_basecaller_b200 import io as xio
+    from xna_basecaller_b200.crf import Model
+    from xna_basecaller_b200.pipeline import basecall_reads
+
+    class Read:
+        def __init__(self, i, raw):
+            self.read_id, self.signal, self.scaling, self.offset = 'raw-%d' % i, raw, RAW_SCALING, -200 + 10 * i
+            self.run_id, self.filename, self.channel, self.mux = 'runA', 'f.fast5', 7 + i, 1
+            self.start, self.duration, self.template_start, self.template_duration = 0.0, 1.0, 0.0, 1.0
+
+    model = Model(sup_config(list('NACGTX')))
+    model.load_state_dict(bo.reference_state_dict(n_base=5, seed=11))
+    model = model.half().eval().to('cuda')
+    reads = [Read(i, synthetic_raw_read(300 + i, n)) for i, n in enumerate((5200, 9100, 3000))]
+    fd = pyio.StringIO()
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        w = xio.Writer('wfq', basecall_reads(model, reads, chunksize=2000, overlap=200, batchsize=8, raw=True), fd=fd,
+                       group_key='sup', summary=os.path.join(tmp, 'summary.tsv'))
+        w.start()
+        w.join()
+        rows = open(os.path.join(tmp, 'summary.tsv')).read().splitlines()
+    lines = fd.getvalue().splitlines()
+    assert len(lines) == 4 * len(reads) and len(rows) == 1 + len(reads)
+    for i, read in enumerate(reads):
+        assert lines[4 * i].startswith('@raw-%d RG:Z:runA_sup\tqs:i:40' % i)
+        seq, qual = lines[4 * i + 1], lines[4 * i + 3]
+        assert len(seq) > 0 and set(seq) <= set('ACGTX') and qual == 'O' * len(seq)
+    assert [x[0] for x in w.log] == [r.read_id for r in reads]

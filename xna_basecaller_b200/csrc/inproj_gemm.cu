@@ -200,6 +200,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t *stg = stgbuf + (set * 4 + q) * STG_BYTES;
+        const uint32_t stg_s = smem_u32(stg);          // explicit shared addressing: through the lambdas the compiler falls back to generic loads / stores
         uint32_t nit = 0;
         bool pending = false;                                  // epilogue of the previous tile's last N tile
         int pend_m0 = 0;
@@ -220,7 +221,6 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
             if (lane == 0) mbar_arrive(&acc_empty[buf]);       // the MMAs of N tile ni+2 may overwrite it now
             if constexpr (EPI == IP_GATES) {
                 const float *bs = sbias + nt * BNI;
-                uint4 *d = reinterpret_cast<uint4 *>(stg + lane * ROW_PITCH);
     #pragma unroll
                 for (int j = 0; j < BNI / 8; j++) {
                     uint32_t pk[4];
@@ -228,7 +228,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                     for (int e = 0; e < 4; e++)
                         pk[e] = X::pack(__uint_as_float(acc[8 * j + 2 * e]) + bs[8 * j + 2 * e],
                                         __uint_as_float(acc[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1]);
-                    d[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    sts_v4(stg_s + lane * ROW_PITCH + j * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 }
                 __syncwarp();
                 const int sub = lane >> 3, l8 = lane & 7;          // 8 lanes x 16 B = one 128-byte row segment
@@ -237,7 +237,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                     const int mm = m0 + q * 32 + rr + sub;
                     if (mm < p.M)
                         reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.out) + (size_t)mm * p.ldo + nt * BNI)[l8] =
-                            *reinterpret_cast<const uint4 *>(stg + (rr + sub) * ROW_PITCH + l8 * 16);
+                            lds_v4(stg_s + (rr + sub) * ROW_PITCH + l8 * 16);
                 }
             } else {
                 // LinearCRFEncoder: scale * tanh(acc + bias), blank score in front of every group of n_base columns; the
@@ -328,10 +328,12 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                 // staging rows and hands each thread its own row for tcgen05.st.
                 const int sub = lane >> 3, l8 = lane & 7;
                 const int mrow0 = m0 + q * 32;
-                constexpr int NBK = KPS;                                 // K blocks in flight per round = one MMA stage
-#pragma unroll 1
-                for (int kb0 = 0; kb0 < KB; kb0 += NBK) {
-                    uint4 ld[NBK][8];
+                // Two K blocks per round, two rounds in flight (register double buffer): the global loads of the next round
+                // are issued before the current one is transposed, so only the first round exposes the L2 / HBM latency.
+                constexpr int NBK = 2;
+                static_assert(KPS == 2 * NBK && KB % KPS == 0, "one a_ready group = two rounds");
+                uint4 ldA[NBK][8], ldB[NBK][8];
+                auto issue = [&](uint4 (&ld)[NBK][8], int kb0) {
 #pragma unroll
                     for (int b = 0; b < NBK; b++)
 #pragma unroll
@@ -340,21 +342,31 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                             ld[b][i] = (mm < p.M) ? __ldg(reinterpret_cast<const uint4 *>(p.x + (size_t)mm * XB_FEATURES + (kb0 + b) * BK) + l8)
                                                   : make_uint4(0, 0, 0, 0);
                         }
+                };
+                auto consume = [&](uint4 (&ld)[NBK][8], int kb0) {
 #pragma unroll
                     for (int b = 0; b < NBK; b++) {
 #pragma unroll
                         for (int i = 0; i < 8; i++)
-                            *reinterpret_cast<uint4 *>(stg + (4 * i + sub) * ROW_PITCH + l8 * 16) = ld[b][i];
+                            sts_v4(stg_s + (4 * i + sub) * ROW_PITCH + l8 * 16, ld[b][i]);
                         __syncwarp();
                         uint32_t v[32];
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            const uint4 t4 = *reinterpret_cast<const uint4 *>(stg + lane * ROW_PITCH + i * 16);
+                            const uint4 t4 = lds_v4(stg_s + lane * ROW_PITCH + i * 16);
                             v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
                         }
                         __syncwarp();
                         tmem_st_32x32b_x32(lane_base + (kb0 + b) * (BK / 2), v);
                     }
+                };
+                issue(ldA, 0);
+#pragma unroll 1
+                for (int kb0 = 0; kb0 < KB; kb0 += KPS) {
+                    issue(ldB, kb0 + NBK);
+                    consume(ldA, kb0);
+                    if (kb0 + KPS < KB) issue(ldA, kb0 + KPS);
+                    consume(ldB, kb0 + NBK);
                     tmem_st_wait();                            // the MMAs of the first N tile start on this group at once
                     tc_fence_before();
                     __syncwarp();

@@ -42,6 +42,14 @@ __device__ __forceinline__ void red_release_gpu_add(int *p, int v) {
 __device__ __forceinline__ void red_relaxed_gpu_add(int *p, int v) {
     asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }

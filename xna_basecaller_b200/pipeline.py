@@ -141,6 +141,23 @@ class ReadSetBasecaller:
                          'seconds_strings': time.perf_counter() - t0 - seconds}
 
 
+def basecall_reads(model, reads, chunksize=4000, overlap=500, batchsize=512, raw=False):
+    """The reference's basecall() contract (crf/basecall.py:96-119) on top of the device-side read-set pipeline: consumes an
+    iterable of read objects (`.read_id`, `.signal`; with raw=True `.signal` holds int16 DAC samples and `.scaling` /
+    `.offset` the channel calibration, fast5.py:64-66) and yields (read, {'sequence', 'qstring', 'sig_move'}) in input order
+    -- the pairs xna_basecaller_b200.io.Writer turns into FASTQ records and summary rows."""
+    reads = list(reads)
+    caller = ReadSetBasecaller(model, chunksize, overlap, batchsize)
+    if raw:
+        strings, _ = caller.basecall([np.asarray(r.signal) for r in reads], scaling=[r.scaling for r in reads],
+                                     offset=[r.offset for r in reads])
+    else:
+        strings, _ = caller.basecall([np.asarray(r.signal) for r in reads])
+    for read, seq in zip(reads, strings):
+        yield read, {'sequence': seq, 'qstring': 'O' * len(seq),
+                     'sig_move': np.zeros(len(read.signal) // caller.stride * caller.stride, dtype=bool)}
+
+
 def basecall_sharded(model, signals, chunksize=4000, overlap=500, batchsize=512, rank=0, world=1):
     """One rank's share of a read set (reads r with r mod world == rank) + the gathered per-rank counters."""
     mine = shard_reads(len(signals), rank, world)
