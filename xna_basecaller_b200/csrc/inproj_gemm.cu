@@ -90,9 +90,13 @@ __device__ __forceinline__ void head_stage64_dyn(const float (&v)[BNI], uint32_t
     }
 }
 
-template <bool BF16, int EPI>
+// XCP: the x block reaches tensor memory as TMA boxes (two K blocks = one 32 KB ring stage, interleaved with the W stages by
+// the producer) copied with tcgen05.cp by the MMA thread, in issue order with its MMAs -- no register / staging-row detour
+// through the epilogue warps, and the next tile's x stages are already in flight while the current tile finishes
+// (tools/tmem_cp_probe.cu checks the copy's layout: lane = row, column c = elements 2c, 2c+1, as the TS-mode MMA reads A).
+template <bool BF16, int EPI, bool XCP>
 __global__ void __launch_bounds__(IPCfg<EPI>::THREADS, 1)
-inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
+inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const IPParams p) {
     using X = xb16<BF16>;
     constexpr int STAGES = IPCfg<EPI>::STAGES, STG_BYTES = IPCfg<EPI>::STG_BYTES;
     const int NT = p.NT;
@@ -137,7 +141,14 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         // ------------------------------------------------------------------ TMA producer: W_ih boxes, all tiles
         if (elect_one()) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (XCP)
+                    for (int xs = 0; xs < KB / 2; xs++, it++) {            // x block: [128 rows x 64 K] x 2 K blocks per stage
+                        const int s = it % STAGES;
+                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                        mbar_expect_tx(&full[s], STAGE_BYTES);
+                        tma_load_3d(smem + s * STAGE_BYTES, &tmX, &full[s], 0, tile * BM, xs * 2);
+                    }
                 for (int nt = 0; nt < NT; nt++)
                     for (int ks = 0; ks < SPT; ks++, it++) {
                         const int s = it % STAGES;
@@ -145,6 +156,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                         mbar_expect_tx(&full[s], STAGE_BYTES);
                         tma_load_3d(smem + s * STAGE_BYTES, &tmW, &full[s], 0, nt * BNI, ks * KPS);
                     }
+            }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -153,6 +165,24 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
         long long st_acc = 0, st_full = 0, st_issue = 0, st_a = 0, tt;
         const bool dbg = p.dbg && blockIdx.x == 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tit++) {
+            if (XCP) {
+                tt = clock64();
+                for (int xs = 0; xs < KB / 2; xs++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t sdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++)             // 2 K blocks x 4 slices of K = 16: 8 tensor-memory columns each
+                            tmem_cp_128x256b(tmem_base + (xs * 2) * (BK / 2) + kk * 8,
+                                             sdesc + (uint64_t)(((kk >> 2) * (BM * BK * 2) + (kk & 3) * 32) >> 4));
+                        mma_commit(&empty[s]);
+                    }
+                    __syncwarp();
+                }
+                st_a += clock64() - tt;
+            }
             for (int nt = 0; nt < NT; nt++, nit++) {
                 const int buf = nit & 1;
                 tt = clock64();
@@ -166,7 +196,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
                     st_full += clock64() - tt;
-                    if (nt == 0) {                             // first N tile: the x block arrives K-block group by group
+                    if (!XCP && nt == 0) {                     // first N tile: the x block arrives K-block group by group
                         tt = clock64();
                         mbar_wait(&a_ready[ks], tit & 1);
                         tc_fence_after();
@@ -316,12 +346,12 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
             const int m0 = tile * BM;
             // all MMAs of the previous tile have completed: its x block may be replaced (set 0), its last accumulator read
             // (the set that owns it; a set never waits on the other set's barrier, it could fall two phases behind)
-            if (pending && (set == 0 || (int)((nit - 1) & 1) == set)) {
+            if (pending && ((!XCP && set == 0) || SETS == 1 || (int)((nit - 1) & 1) == set)) {
                 mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);
                 tc_fence_after();
             }
             const long long tl0 = clock64();
-            if (valid && set == 0) {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
+            if (!XCP && valid && set == 0) {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
                 // during this, so it has to be quick: a direct row-per-thread read costs one L1 wavefront per lane
                 // (12 k wavefronts per tile, ~20 k cycles).  Instead a warp reads its 32 rows coalesced, 128 bytes
                 // (= one K block) of four rows per instruction, four K blocks in flight, transposes through its
@@ -417,8 +447,10 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const IPParams p) {
 
 template <int EPI>
 static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaStream_t s) {
-    CUtensorMap tmW;
+    CUtensorMap tmW, tmX;
     if (int rc = xb_make_tmap_hview(h, &tmW, w, w_rows, BNI, KPS)) return rc;
+    if (int rc = xb_make_tmap_hview(h, &tmX, p.x, (uint64_t)p.M, BM, 2)) return rc;
+    static const bool regload = getenv("XB_INPROJ_REGLOAD") != nullptr;     // the earlier x path through registers / staging rows
     p.NT = w_rows / BNI;
     p.dbg = nullptr;
     p.no_prefetch = getenv("XB_INPROJ_NOPF") ? 1 : 0;
@@ -430,21 +462,20 @@ static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaSt
     const int ntiles = (p.M + BM - 1) / BM;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
     constexpr int SMEM_BYTES = IPCfg<EPI>::SMEM_BYTES;
-    static bool configured[2][64] = {};   // per device: function attributes live in the device's context
+    static bool configured[4][64] = {};   // per device: function attributes live in the device's context
     const int dv = h->device & 63;
-    if (h->bf16) {
-        if (!configured[1][dv]) {
-            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[1][dv] = true;
+    auto go = [&](auto kernel, int slot) -> int {
+        if (!configured[slot][dv]) {
+            XB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            configured[slot][dv] = true;
         }
-        inproj_kernel<true, EPI><<<grid, IPCfg<EPI>::THREADS, SMEM_BYTES, s>>>(tmW, p);
-    } else {
-        if (!configured[0][dv]) {
-            XB_CUDA(h, cudaFuncSetAttribute(inproj_kernel<false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured[0][dv] = true;
-        }
-        inproj_kernel<false, EPI><<<grid, IPCfg<EPI>::THREADS, SMEM_BYTES, s>>>(tmW, p);
-    }
+        kernel<<<grid, IPCfg<EPI>::THREADS, SMEM_BYTES, s>>>(tmW, tmX, p);
+        return XB_OK;
+    };
+    int rc;
+    if (h->bf16) rc = regload ? go(inproj_kernel<true, EPI, false>, 0) : go(inproj_kernel<true, EPI, true>, 1);
+    else rc = regload ? go(inproj_kernel<false, EPI, false>, 2) : go(inproj_kernel<false, EPI, true>, 3);
+    if (rc) return rc;
     XB_LAUNCH_CHECK(h);
     if (p.dbg) {
         long long v[8];
