@@ -1,6 +1,6 @@
 """BASELINE config 4 (scaled): synthetic read set sharded by read across the ranks of one box.
 
-    python tools/run_readset.py [n_reads]                       # 1 GPU
+    python tools/run_readset.py [n_reads] [--raw]               # 1 GPU; --raw: int16 DAC reads, pre-processed on the GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
         tools/run_readset.py [n_reads]
 
@@ -30,7 +30,9 @@ def sup_config(alphabet):
                         'rnn_type': 'lstm', 'blank_score': 2.0}}
 
 
-n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+RAW = '--raw' in sys.argv
+args = [a for a in sys.argv[1:] if not a.startswith('--')]
+n_reads = int(args[0]) if args else 4000
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
 torch.cuda.set_device(local)
 if world > 1:
@@ -42,15 +44,22 @@ model.load_state_dict(bo.reference_state_dict(n_base=5, seed=25))
 model = model.half().eval().to('cuda:%d' % local)
 mine = pipeline.shard_reads(n_reads, rank, world)
 g = np.random.RandomState(1000 + rank)
-signals = [g.standard_normal(int(lengths[i])).astype(np.float32) for i in mine]
 caller = pipeline.ReadSetBasecaller(model, 4000, 500, 512)
-caller.basecall(signals)                                # warm-up (handle, weights, pinned staging buffers)
-strings, counters = caller.basecall(signals)
+if RAW:        # int16 DAC samples (2 B/sample over PCIe) + per-read calibration; scaling, trim, med/MAD on the GPU
+    signals = [np.clip(np.round(400 + 40 * g.standard_normal(int(lengths[i])) +
+                                np.repeat(25 * g.standard_normal(int(lengths[i]) // 8 + 1), 8)[:int(lengths[i])]),
+                       -2000, 2000).astype(np.int16) for i in mine]
+    kw = {'scaling': np.full(len(mine), 1437.976 / 8192), 'offset': g.randint(-300, 300, len(mine))}
+else:
+    signals = [g.standard_normal(int(lengths[i])).astype(np.float32) for i in mine]
+    kw = {}
+caller.basecall(signals, **kw)                          # warm-up (handle, weights, pinned staging buffers)
+strings, counters = caller.basecall(signals, **kw)
 table = pipeline.gather_counters(counters, device=torch.device('cuda', local) if world > 1 else None)
 if rank == 0:
     total = sum(table['samples'])
     sec = max(table['seconds'])
-    print(json.dumps({'config': 'configs[3] scaled: %d reads, cs 4000, ov 500, batch 512, sharded r mod G' % n_reads,
+    print(json.dumps({'config': 'configs[3] scaled: %d reads%s, cs 4000, ov 500, batch 512, sharded r mod G' % (n_reads, ' (raw int16 + GPU pre-processing)' if RAW else ''),
                       'n_gpus': world, 'samples': total, 'seconds_max_rank': sec, 'samples_per_s': total / sec,
                       'chunks': sum(table['chunks']), 'reads_per_rank': table['reads'],
                       'rank0_seconds': {k: v[0] for k, v in table.items() if k.startswith('seconds_')},
