@@ -11,12 +11,18 @@
 // One CTA per SM, persistent over M tiles (tile = blockIdx.x, += gridDim.x).  Per M tile: 48 N tiles of 64
 // gate columns; two 64-column fp32 accumulators in the remaining 128 TMEM columns, so the epilogue of N tile i
 // (TMEM -> +bias -> 16-bit -> staged rows -> 128-byte row segments of G) overlaps the MMAs of N tile i+1.
-// W_ih arrives as 3-D TMA boxes of four [64 rows x 64 K] 128B-swizzled blocks (32 KB) through a 4-stage ring
-// (128 KB in flight); one mbarrier wait and one commit per 16 MMAs keep the single issuing thread ahead of
-// the tensor pipe (with one wait per 4 MMAs the issue loop, not the pipe, set the pace).
+// W_ih arrives as 3-D TMA boxes of four [64 rows x 64 K] 128B-swizzled blocks (32 KB) through a 6-stage ring
+// (192 KB in flight); one mbarrier wait and one commit per 16 MMAs keep the single issuing thread ahead of
+// the tensor pipe (with one wait per 4 MMAs the issue loop, not the pipe, set the pace).  The x block travels through
+// the same ring (six stages of two [128 rows x 64 K] blocks in front of every tile's W stages) and is copied into
+// tensor memory with tcgen05.cp by the MMA thread, in issue order with its MMAs.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 load the
-// x block into TMEM (thread = row) and run the epilogues (warp % 4 = TMEM lane quarter).
+// The same kernel with the IP_SCORES epilogue is the CRF head (LinearCRFEncoder, nn.py:87-133): W_head streams instead
+// of W_ih, fp32 score rows with the blank score inserted leave as coalesced segments, two epilogue warp sets.
+//
+// Warp roles (256 threads; 384 for IP_SCORES): warp 0 TMA producer, warp 1 MMA issuer (+ tcgen05.cp of the x block),
+// warp 2 TMEM allocator, warps 4..7 (and 8..11) run the epilogues (warp % 4 = TMEM lane quarter).  XB_INPROJ_REGLOAD=1
+// selects the earlier x path (epilogue warps load the rows, transpose them through staging rows, tcgen05.st).
 #include <stdlib.h>
 
 #include "xb_common.cuh"
