@@ -31,7 +31,8 @@
 // MMAs part by part as the boxes land, commit; plus the G prefetch), warp SUB allocates tensor memory, epilogue
 // warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
 // quarter; the second four take the upper half of the chunk columns).  XB_LSTM_VARIANT selects the measured
-// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks), XB_LSTM_WARP_RELEASE=1 the per-warp release.
+// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks, 3: two of 48 chunks with twelve epilogue warps),
+// XB_LSTM_WARP_RELEASE=1 the per-warp release.
 #include <stdlib.h>
 
 #include "xb_common.cuh"
@@ -68,8 +69,8 @@ template <int SUB, int NS, int EW> struct Cfg {          // EW = epilogue warps 
     static constexpr int STAGE_BYTES = NC * 16;               // per epilogue warp: [chunk][8 units] 16-bit
     static constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + SUB * EW * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
     static_assert(D_COL + SUB * NS <= 512, "tensor memory columns");
-    static_assert(NS % 16 == 0 && NS <= 32, "MMA N");
-    static_assert((EW == 4 || EW == 8) && NC % 16 == 0, "epilogue split");
+    static_assert(NS % 16 == 0 && NS <= 48, "MMA N");
+    static_assert((EW == 4 || EW == 8 || EW == 12) && NC % 16 == 0, "epilogue split");
     static_assert(SUB * NBAR * 8 + 16 <= 1024, "barrier block");
     static_assert(H_BLOCK_BYTES % 1024 == 0, "swizzle atom alignment");
 };
@@ -466,6 +467,9 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
     if (variant == 1)
         return h->bf16 ? launch_cfg<true, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s)
                        : launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
+    if (variant == 3)
+        return h->bf16 ? launch_cfg<true, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s)
+                       : launch_cfg<false, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s);
     if (variant == 2)
         return h->bf16 ? launch_cfg<true, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s)
                        : launch_cfg<false, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s);
