@@ -76,17 +76,25 @@ def summary_row(read, seqlen, qscore, alignment=False):
 
 
 class CSVLogger:
-    """Append-mode delimited table: the header is taken from an existing file, else from the first row's keys."""
+    """Delimited table opened for appending.  A file that already has content keeps its header row (new rows are aligned to
+    it, missing keys become '-'); a new file gets the keys of the first appended row as header.  Rows are flushed in
+    batches of ~100 and on close.  Behaviour of bonito/io.py:322-356."""
+
+    FLUSH_EVERY = 100
 
     def __init__(self, filename, sep=','):
-        self.filename = str(filename)
-        self.columns = None
-        if os.path.exists(self.filename):
-            with open(self.filename) as f:
-                self.columns = csv.DictReader(f, delimiter=sep).fieldnames
+        self.filename, self.sep = str(filename), sep
+        self.columns = self._existing_header()
         self.fh = open(self.filename, 'a', newline='')
         self.csvwriter = csv.writer(self.fh, delimiter=sep)
-        self.count = 0
+        self._unflushed = 0
+
+    def _existing_header(self):
+        if not os.path.exists(self.filename):
+            return None
+        with open(self.filename, newline='') as f:
+            first = next(csv.reader(f, delimiter=self.sep), None)
+        return first or None
 
     def set_columns(self, columns):
         if self.columns:
@@ -97,11 +105,11 @@ class CSVLogger:
     def append(self, row):
         if self.columns is None:
             self.set_columns(row.keys())
-        self.csvwriter.writerow([row.get(k, '-') for k in self.columns])
-        self.count += 1
-        if self.count > 100:
-            self.count = 0
+        self.csvwriter.writerow([row.get(name, '-') for name in self.columns])
+        self._unflushed += 1
+        if self._unflushed > self.FLUSH_EVERY:
             self.fh.flush()
+            self._unflushed = 0
 
     def close(self):
         self.fh.close()
@@ -109,7 +117,7 @@ class CSVLogger:
     def __enter__(self):
         return self
 
-    def __exit__(self, *args):
+    def __exit__(self, *exc):
         self.close()
 
 

@@ -26,19 +26,34 @@ layers = {}
 FEATURES = 768
 
 
-def register(layer):
-    layer.name = layer.__name__.lower()
-    layers[layer.name] = layer
-    return layer
+def register(cls):
+    """Class decorator: file `cls` in the registry under its lower-cased class name (the `type` of config dicts)."""
+    key = cls.__name__.lower()
+    cls.name = key
+    layers[key] = cls
+    return cls
 
 
-register(torch.nn.ReLU)
-register(torch.nn.Tanh)
+for _activation in (torch.nn.ReLU, torch.nn.Tanh):
+    register(_activation)
 
 
 @register
 class Swish(torch.nn.SiLU):
-    pass
+    """x * sigmoid(x); the name the reference's configs use for SiLU."""
+
+
+def _activation_from(spec):
+    """Registry name -> fresh module; anything else (None, a module) is passed through."""
+    return layers[spec]() if spec in layers else spec
+
+
+def _name_of(activation):
+    return activation.name if activation else None
+
+
+def _weights(weight, bias, w_key='W', b_key='b'):
+    return {w_key: weight, b_key: [] if bias is None else bias}
 
 
 def _engine_of(module):
@@ -151,7 +166,10 @@ class Reverse(Module):
 
     def __init__(self, sublayers):
         super().__init__()
-        self.layer = Serial(sublayers) if isinstance(sublayers, list) else sublayers
+        wrapped = sublayers
+        if isinstance(wrapped, list):
+            wrapped = Serial(wrapped)
+        self.layer = wrapped
 
     def forward(self, x):
         inner = self.layer
@@ -160,9 +178,8 @@ class Reverse(Module):
         return inner(x.flip(0)).flip(0)
 
     def to_dict(self, include_weights=False):
-        if isinstance(self.layer, Serial):
-            return self.layer.to_dict(include_weights)
-        return {'sublayers': to_dict(self.layer, include_weights)}
+        inner = self.layer
+        return inner.to_dict(include_weights) if isinstance(inner, Serial) else {'sublayers': to_dict(inner, include_weights)}
 
 
 @register
@@ -170,8 +187,9 @@ class Convolution(Module):
 
     def __init__(self, insize, size, winlen, stride=1, padding=0, bias=True, activation=None):
         super().__init__()
-        self.conv = torch.nn.Conv1d(insize, size, winlen, stride=stride, padding=padding, bias=bias)
-        self.activation = layers.get(activation, lambda: activation)()
+        self.activation = _activation_from(activation)
+        self.conv = torch.nn.Conv1d(in_channels=insize, out_channels=size, kernel_size=winlen, stride=stride,
+                                    padding=padding, bias=bias)
 
     def forward(self, x):
         raise RuntimeError(
@@ -180,18 +198,13 @@ class Convolution(Module):
             'there is no stand-alone or CPU convolution on this path')
 
     def to_dict(self, include_weights=False):
-        res = {
-            'insize': self.conv.in_channels,
-            'size': self.conv.out_channels,
-            'bias': self.conv.bias is not None,
-            'winlen': self.conv.kernel_size[0],
-            'stride': self.conv.stride[0],
-            'padding': self.conv.padding[0],
-            'activation': self.activation.name if self.activation else None,
-        }
+        c = self.conv
+        (winlen,), (stride,), (padding,) = c.kernel_size, c.stride, c.padding
+        out = dict(insize=c.in_channels, size=c.out_channels, bias=c.bias is not None, winlen=winlen, stride=stride,
+                   padding=padding, activation=_name_of(self.activation))
         if include_weights:
-            res['params'] = {'W': self.conv.weight, 'b': self.conv.bias if self.conv.bias is not None else []}
-        return res
+            out['params'] = _weights(c.weight, c.bias)
+        return out
 
 
 @register
@@ -200,18 +213,17 @@ class LinearCRFEncoder(Module):
     def __init__(self, insize, n_base, state_len, bias=True, scale=None, activation=None, blank_score=None,
                  expand_blanks=True, extra_linear=False, drop_rate=0):
         super().__init__()
-        self.scale = scale
-        self.n_base = n_base
-        self.state_len = state_len
-        self.blank_score = blank_score
-        self.expand_blanks = expand_blanks
+        self.n_base, self.state_len = n_base, state_len
+        self.scale, self.blank_score, self.expand_blanks = scale, blank_score, expand_blanks
+        # a learnt blank column per state unless the blank score is a constant: C * (n + 1) or C * n outputs
+        states = n_base ** state_len
+        width = states * n_base if blank_score is not None else states * (n_base + 1)
         self.extra_linear = extra_linear
         if extra_linear:
             self.linear_ext = torch.nn.Linear(insize, insize, bias=bias)
         self.dropout = torch.nn.Dropout(p=drop_rate)
-        size = (n_base + 1) * n_base ** state_len if blank_score is None else n_base ** (state_len + 1)
-        self.linear = torch.nn.Linear(insize, size, bias=bias)
-        self.activation = layers.get(activation, lambda: activation)()
+        self.linear = torch.nn.Linear(insize, width, bias=bias)
+        self.activation = _activation_from(activation)
 
     def forward(self, x):
         if self.extra_linear:
@@ -240,21 +252,14 @@ class LinearCRFEncoder(Module):
             self.linear.weight, self.linear.bias, self.scale, self.blank_score, self.expand_blanks))
 
     def to_dict(self, include_weights=False):
-        res = {
-            'insize': self.linear.in_features,
-            'n_base': self.n_base,
-            'state_len': self.state_len,
-            'bias': self.linear.bias is not None,
-            'scale': self.scale,
-            'activation': self.activation.name if self.activation else None,
-            'blank_score': self.blank_score,
-        }
+        lin = self.linear
+        out = dict(insize=lin.in_features, n_base=self.n_base, state_len=self.state_len, bias=lin.bias is not None,
+                   scale=self.scale, activation=_name_of(self.activation), blank_score=self.blank_score)
         if include_weights:
-            res['params'] = {'W': self.linear.weight, 'b': self.linear.bias if self.linear.bias is not None else []}
+            out['params'] = _weights(lin.weight, lin.bias)
             if self.extra_linear:
-                res['params']['W_ext'] = self.linear_ext.weight
-                res['params']['b_ext'] = self.linear_ext.bias if self.linear_ext.bias is not None else []
-        return res
+                out['params'].update(_weights(self.linear_ext.weight, self.linear_ext.bias, 'W_ext', 'b_ext'))
+        return out
 
 
 @register
@@ -264,17 +269,21 @@ class Permute(Module):
         super().__init__()
         self.dims = dims
 
+    def extra_repr(self):
+        return 'dims=%s' % (list(self.dims),)
+
     def forward(self, x):
-        return x.permute(*self.dims)
+        return torch.permute(x, tuple(self.dims))
 
     def to_dict(self, include_weights=False):
-        return {'dims': self.dims}
+        return dict(dims=self.dims)
 
 
 def truncated_normal(size, dtype=torch.float32, device=None, num_resample=5):
-    x = torch.empty(size + (num_resample,), dtype=torch.float32, device=device).normal_()
-    i = ((x < 2) & (x > -2)).max(-1, keepdim=True)[1]
-    return torch.clamp_(x.gather(-1, i).squeeze(-1), -2, 2)
+    """Standard normal samples restricted to (-2, 2) (nn.py:170-173 draws `num_resample` candidates per element and keeps
+    the first inside the interval; torch's trunc_normal_ samples the same distribution directly)."""
+    out = torch.empty(tuple(size), dtype=dtype, device=device)
+    return torch.nn.init.trunc_normal_(out, mean=0.0, std=1.0, a=-2.0, b=2.0)
 
 
 class RNNWrapper(Module):
@@ -284,14 +293,18 @@ class RNNWrapper(Module):
     def __init__(self, rnn_type, *args, reverse=False, orthogonal_weight_init=True, disable_state_bias=True,
                  bidirectional=False, **kwargs):
         super().__init__()
-        if reverse and bidirectional:
+        if bidirectional and reverse:
             raise Exception("'reverse' and 'bidirectional' should not both be set to True")
-        self.reverse = reverse
         self.rnn = rnn_type(*args, bidirectional=bidirectional, **kwargs)
+        self.reverse = reverse
         self.init_orthogonal(orthogonal_weight_init)
         self.init_biases()
         if disable_state_bias:
             self.disable_state_bias()
+
+    def _params_named(self, fragments):
+        """Parameters of the wrapped RNN whose name contains one of `fragments`."""
+        return [(n, q) for n, q in self.rnn.named_parameters() if any(f in n for f in fragments)]
 
     def forward(self, x, reverse=None):
         rnn = self.rnn
@@ -313,26 +326,28 @@ class RNNWrapper(Module):
         eng.sync(('lstm', slot), w, lambda hd: hd.load_lstm_weights(slot, *w))
 
     def init_biases(self, types=('bias_ih',)):
-        for name, param in self.rnn.named_parameters():
-            if any(k in name for k in types):
-                with torch.no_grad():
-                    param.set_(0.5 * truncated_normal(param.shape, dtype=param.dtype, device=param.device))
+        """Input biases ~ 0.5 * N(0, 1) truncated to (-2, 2) (nn.py:195-199)."""
+        with torch.no_grad():
+            for _, q in self._params_named(types):
+                q.copy_(truncated_normal(q.shape, dtype=q.dtype, device=q.device).mul_(0.5))
 
     def init_orthogonal(self, types=True):
-        if not types:
-            return
+        """Every (hidden x in) gate block of the selected weight matrices gets its own orthogonal init (nn.py:201-207)."""
         if types is True:
             types = ('weight_ih', 'weight_hh')
-        for name, x in self.rnn.named_parameters():
-            if any(k in name for k in types):
-                for i in range(0, x.size(0), self.rnn.hidden_size):
-                    orthogonal_(x[i:i + self.rnn.hidden_size])
+        if not types:
+            return
+        H = self.rnn.hidden_size
+        for _, q in self._params_named(types):
+            for gate_block in q.split(H, dim=0):
+                orthogonal_(gate_block)
 
     def disable_state_bias(self):
-        for name, x in self.rnn.named_parameters():
-            if 'bias_hh' in name:
-                x.requires_grad = False
-                x.zero_()
+        """bias_hh is frozen at zero: only bias_ih is learnt, but the parameter stays in the state_dict (nn.py:209-213)."""
+        for _, q in self._params_named(('bias_hh',)):
+            q.requires_grad_(False)
+            with torch.no_grad():
+                q.zero_()
 
 
 @register
@@ -342,39 +357,32 @@ class LSTM(RNNWrapper):
         super().__init__(torch.nn.LSTM, size, insize, bias=bias, reverse=reverse)
 
     def to_dict(self, include_weights=False):
-        res = {
-            'size': self.rnn.hidden_size,
-            'insize': self.rnn.input_size,
-            'bias': self.rnn.bias,
-            'reverse': self.reverse,
-        }
-        if include_weights:
-            H, I = self.rnn.hidden_size, self.rnn.input_size
-            res['params'] = {
-                'iW': self.rnn.weight_ih_l0.reshape(4, H, I),
-                'sW': self.rnn.weight_hh_l0.reshape(4, H, H),
-                'b': self.rnn.bias_ih_l0.reshape(4, H),
-            }
-        return res
+        r = self.rnn
+        out = dict(size=r.hidden_size, insize=r.input_size, bias=r.bias, reverse=self.reverse)
+        if include_weights:       # per-gate views: input weights, state weights, input bias (bias_hh is identically zero)
+            out['params'] = dict(iW=r.weight_ih_l0.view(4, r.hidden_size, r.input_size),
+                                 sW=r.weight_hh_l0.view(4, r.hidden_size, r.hidden_size),
+                                 b=r.bias_ih_l0.view(4, r.hidden_size))
+        return out
 
 
 def to_dict(layer, include_weights=False):
-    if hasattr(layer, 'to_dict'):
-        return {'type': layer.name, **layer.to_dict(include_weights)}
-    return {'type': layer.name}
+    """{'type': registry name, **the layer's own description}."""
+    described = layer.to_dict(include_weights) if hasattr(layer, 'to_dict') else {}
+    return dict(type=layer.name, **described)
 
 
 def from_dict(model_dict, layer_types=None):
-    model_dict = model_dict.copy()
-    if layer_types is None:
-        layer_types = layers
-    type_name = model_dict.pop('type')
-    typ = layer_types[type_name]
-    if 'sublayers' in model_dict:
-        sub = model_dict['sublayers']
-        model_dict['sublayers'] = [from_dict(x, layer_types) for x in sub] if isinstance(sub, list) \
-            else from_dict(sub, layer_types)
+    """Inverse of to_dict: build the module tree a (new-style) config describes."""
+    registry = layers if layer_types is None else layer_types
+    kwargs = {k: v for k, v in model_dict.items() if k != 'type'}
+    cls = registry[model_dict['type']]
+    nested = kwargs.get('sublayers')
+    if isinstance(nested, list):
+        kwargs['sublayers'] = [from_dict(d, registry) for d in nested]
+    elif nested is not None:
+        kwargs['sublayers'] = from_dict(nested, registry)
     try:
-        return typ(**model_dict)
+        return cls(**kwargs)
     except Exception as e:
-        raise Exception(f'Failed to build layer of type {typ} with args {model_dict}') from e
+        raise Exception('Failed to build layer of type %s with args %s' % (cls, kwargs)) from e
