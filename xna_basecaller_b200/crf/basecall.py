@@ -75,31 +75,38 @@ def to_str(x):
 
 
 def apply_stride_to_moves(model, attrs):
-    moves = np.array(attrs['moves'], dtype=bool)
-    sig_move = np.full(moves.size * model.stride, False)
-    sig_move[np.where(moves)[0] * model.stride] = True
-    return {
-        'qstring': to_str(attrs['qstring']),
-        'sequence': to_str(attrs['sequence']),
-        'sig_move': sig_move,
-    }
+    """Stitched per-read arrays -> the record the Writer consumes: letters and qualities as ascii strings (zeros dropped),
+    and the move table spread onto sample positions (one flag per signal sample, set at the first sample of a step that
+    emitted a base; all False for the UB models, whose decode carries no moves)."""
+    step_moved = np.asarray(attrs['moves']).astype(bool)
+    sig_move = np.zeros(step_moved.size * model.stride, dtype=bool)
+    sig_move[np.flatnonzero(step_moved) * model.stride] = True
+    return dict(sequence=to_str(attrs['sequence']), qstring=to_str(attrs['qstring']), sig_move=sig_move)
 
 
 def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=False):
-    """Basecalls a set of reads: iterator of (read, {'sequence', 'qstring', 'sig_move'}) in input order."""
-    chunks = thread_iter(
-        ((read, 0, len(read.signal)), chunk(torch.from_numpy(read.signal), chunksize, overlap))
-        for read in reads
-    )
-    batches = thread_iter(batchify(chunks, batchsize=batchsize))
-    scores = thread_iter(
-        (read, compute_scores(model, batch, reverse=reverse)) for read, batch in batches
-    )
-    results = thread_iter(
-        (read, stitch_results(scores, end - start, chunksize, overlap, model.stride, reverse))
-        for ((read, start, end), scores) in unbatchify(scores)
-    )
-    return thread_iter(
-        (read, apply_stride_to_moves(model, attrs))
-        for read, attrs in results
-    )
+    """Basecalls a set of reads: iterator of (read, {'sequence', 'qstring', 'sig_move'}) in input order.
+
+    Four stages, each drained by its own background thread through a depth-1 queue (thread_iter), as in the reference:
+    reads -> chunk tensors keyed (read, 0, n_samples) -> exact-size batches -> compute_scores on the GPU -> regrouped per
+    read, stitched, converted to strings."""
+
+    def chunked():
+        for read in reads:
+            yield (read, 0, len(read.signal)), chunk(torch.from_numpy(read.signal), chunksize, overlap)
+
+    def scored(batches):
+        for keys, batch in batches:
+            yield keys, compute_scores(model, batch, reverse=reverse)
+
+    def stitched(per_read):
+        for (read, start, end), parts in per_read:
+            yield read, stitch_results(parts, end - start, chunksize, overlap, model.stride, reverse)
+
+    def finished(results):
+        for read, attrs in results:
+            yield read, apply_stride_to_moves(model, attrs)
+
+    batches = thread_iter(batchify(thread_iter(chunked()), batchsize=batchsize))
+    per_read = unbatchify(thread_iter(scored(batches)))
+    return thread_iter(finished(thread_iter(stitched(per_read))))
