@@ -203,3 +203,23 @@ def test_training_forward_loss_config5():
     np.testing.assert_allclose(loss[pick].numpy(), same.numpy(), rtol=5e-5)
     np.testing.assert_allclose(loss[pick].numpy(), ref.numpy(), rtol=3e-2)
     h.close()
+
+
+def test_batch_position_independence_odd_sizes():
+    """A chunk's scores and decode do not depend on where it sits in the batch or on the batch size: batches of odd sizes
+    (uneven LSTM groups and sub-batches, partial GEMM tiles, a second recurrence launch at N > 576) built by repeating five
+    chunks give, for every copy, the bits of the five-chunk batch."""
+    from xna_basecaller_b200._lib import Handle
+    T, L = 120, 600
+    h = Handle(ALPHABETS[5], 3, max_N=1000, max_T=T)
+    h.load_weights(bo.reference_state_dict(n_base=5, seed=11))
+    base = synthetic_signal(33, 5, L)[:, 0, :].contiguous().cuda()
+    s0 = h.encoder(base)
+    seq0, _, lens0 = h.decode(s0, want_qstring=False)
+    for N in (1, 7, 97, 300, 577, 1000):
+        idx = torch.arange(N, device='cuda') % 5
+        s = h.encoder(base[idx].contiguous())
+        assert torch.equal(s, s0[:, idx]), N
+        seq, _, lens = h.decode(s, want_qstring=False)
+        assert torch.equal(seq, seq0[idx]) and torch.equal(lens, lens0[idx]), N
+    h.close()
