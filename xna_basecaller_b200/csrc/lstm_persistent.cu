@@ -31,7 +31,8 @@
 // MMAs part by part as the boxes land, commit; plus the G prefetch), warp SUB allocates tensor memory, epilogue
 // warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
 // quarter; the second four take the upper half of the chunk columns).  XB_LSTM_VARIANT selects the measured
-// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks, 3: two of 48 chunks with twelve epilogue warps),
+// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks, 3: two of 48 chunks with twelve epilogue warps,
+// 4: four of 32 chunks with four epilogue warps each and a single G buffer per sub-batch -- 96 CTAs at N = 512),
 // XB_LSTM_WARP_RELEASE=1 the per-warp release.
 #include <stdlib.h>
 
@@ -56,7 +57,7 @@ constexpr int D_COL = 384;                 // accumulators start after the 384 c
 constexpr int CTR_STRIDE = 32;             // ints between counters (one 128-byte line each)
 constexpr int MAX_CTRS = 64;
 
-template <int SUB, int NS, int EW> struct Cfg {          // EW = epilogue warps per sub-batch (4 or 8)
+template <int SUB, int NS, int EW, int GB = 2> struct Cfg {  // EW = epilogue warps per sub-batch; GB = G buffers per sub-batch
     static constexpr int NB = SUB * NS;                       // chunks per group
     static constexpr int H_BLOCK_BYTES = NS * 64 * 2;         // one K block: NS rows x 128 B
     static constexpr int H_PART_BYTES = KPB * H_BLOCK_BYTES;
@@ -67,7 +68,9 @@ template <int SUB, int NS, int EW> struct Cfg {          // EW = epilogue warps 
     static constexpr int THREADS = (EPI_WARP0 + EW * SUB) * 32;
     static constexpr int NC = NS * 4 / EW;                    // accumulator columns (chunks) per epilogue warp
     static constexpr int STAGE_BYTES = NC * 16;               // per epilogue warp: [chunk][8 units] 16-bit
-    static constexpr int SMEM_BYTES = SUB * (H_BYTES + 2 * G_BYTES) + SUB * EW * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    // GB == 1 (four-chain variant): one G buffer per sub-batch, refilled after the epilogue has consumed it, and the h-slice
+    // staging rows alias the bytes of it that the same warp read -- 4 x (48 + 8) KB + barriers just fit 227 KB
+    static constexpr int SMEM_BYTES = SUB * (H_BYTES + GB * G_BYTES) + (GB == 2 ? SUB * EW * STAGE_BYTES : 0) + 1024 /*align*/ + 1024 /*barriers*/;
     static_assert(D_COL + SUB * NS <= 512, "tensor memory columns");
     static_assert(NS % 16 == 0 && NS <= 48, "MMA N");
     static_assert((EW == 4 || EW == 8 || EW == 12) && NC % 16 == 0, "epilogue split");
@@ -121,17 +124,17 @@ template <> __device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, u
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
-template <bool BF16, int SUB, int NS, int EW>
-__global__ void __launch_bounds__(Cfg<SUB, NS, EW>::THREADS, 1)
+template <bool BF16, int SUB, int NS, int EW, int GB>
+__global__ void __launch_bounds__(Cfg<SUB, NS, EW, GB>::THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
     using X = xb16<BF16>;
-    using C = Cfg<SUB, NS, EW>;
+    using C = Cfg<SUB, NS, EW, GB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *hbuf = smem;                                       // [SUB][H_BYTES]
-    uint8_t *gbuf = smem + SUB * C::H_BYTES;                    // [SUB][2][G_BYTES]
-    uint8_t *stage = gbuf + SUB * 2 * C::G_BYTES;               // [SUB][EW][STAGE_BYTES]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + SUB * EW * C::STAGE_BYTES);
+    uint8_t *gbuf = smem + SUB * C::H_BYTES;                    // [SUB][GB][G_BYTES]
+    uint8_t *stage = gbuf + SUB * GB * C::G_BYTES;              // [SUB][EW][STAGE_BYTES] (GB == 2 only)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (GB == 2 ? SUB * EW * C::STAGE_BYTES : 0));
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + SUB * C::NBAR);
     auto h_full = [&](int sub, int part) { return bars + sub * C::NBAR + part; };
     auto d_full = [&](int sub) { return bars + sub * C::NBAR + HP; };
@@ -205,10 +208,10 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(hb));
             const uint32_t dcol = tmem_base + D_COL + sub * NS;
             mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
-            tma_load_2d(gbuf + (sub * 2) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
+            tma_load_2d(gbuf + (sub * GB) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
             for (int s = 0; s < T; s++) {
                 const int t = p.reverse ? T - 1 - s : s;
-                if (s + 1 < T) {      // input projection of the next step, one step ahead
+                if (GB == 2 && s + 1 < T) {      // input projection of the next step, one step ahead
                     const int sn = s + 1, q = sn & 1, u = sn >> 1;
                     const int tn = p.reverse ? T - 1 - sn : sn;
                     if (u >= 1) mbar_wait(g_empty(sub, q), (u - 1) & 1);
@@ -262,6 +265,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     mma_commit(d_full(sub));
                     DBG(sub, 4);
                 }
+                if (GB == 1 && s + 1 < T) {      // single G buffer: refill once this step's epilogue is through with it
+                    const int tn = p.reverse ? T - 2 - s : s + 1;
+                    mbar_wait(g_empty(sub, 0), s & 1);
+                    mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
+                    tma_load_2d(gbuf + sub * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, tn * N + row0);
+                }
             }
         }
     } else if (warp >= C::EPI_WARP0) {
@@ -282,7 +291,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 
         for (int s = 0; s < T; s++) {
             const int t = p.reverse ? T - 1 - s : s;
-            const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * 2 + (s & 1)) * C::G_BYTES);
+            const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * GB + (GB == 2 ? (s & 1) : 0)) * C::G_BYTES);
             // Accumulator -> registers with tcgen05.ld.16x256b: thread (a = lane/4, b = lane%4) receives rows a, a+8 (first
             // load) and a+16, a+24 (second load, 16 lanes further) of columns 8k+2b, 8k+2b+1.  The rows of a lane quarter are
             // ordered gate*8 + unit, so those four rows are i, f, g, o of unit a: the load itself delivers whole cells
@@ -290,7 +299,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             // The input projection of the step arrived a step ago: fetch it from shared memory BEFORE waiting for the
             // accumulator, so only the adds remain on the serial chain.
             // cell m of the thread: chunk 8*(m/2) + 2b + m%2 (relative to col0), unit ul
-            mbar_wait(g_full(sub, s & 1), (s >> 1) & 1);
+            mbar_wait(g_full(sub, GB == 2 ? (s & 1) : 0), GB == 2 ? ((s >> 1) & 1) : (s & 1));
             float pre[CELLS][4];
 #pragma unroll
             for (int m = 0; m < CELLS; m++) {
@@ -373,16 +382,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             if (ew == 0 && lane == 0) DBG(sub, 7);
             // h slice of the warp (NS chunks x 8 units) through a 16 B-per-chunk staging row: one 16-byte global
             // store per chunk instead of eight 2-byte ones
-            uint16_t *st = reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES));
+            // GB == 2: private staging rows.  GB == 1: the rows alias the 16 bytes at the head of the 64-byte G segments this
+            // warp itself read above (chunk rows col0.., unit columns q*8..), so no other warp's data is touched.
+            constexpr int ST_PITCH = GB == 2 ? 8 : 128;          // 16-bit elements between consecutive chunks
+            uint16_t *st = GB == 2 ? reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES))
+                                   : const_cast<uint16_t *>(Gs) + col0 * 128 + q * 32;
+            if (GB == 1) __syncwarp();                           // every lane has taken its G values
 #pragma unroll
             for (int i = 0; i < CELLS; i++) {
                 typename X::T hv = X::from(hout[i]);
-                st[(8 * (i >> 1) + 2 * gt + (i & 1)) * 8 + ul] = *reinterpret_cast<uint16_t *>(&hv);
+                st[(8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul] = *reinterpret_cast<uint16_t *>(&hv);
             }
             __syncwarp();
             if (lane < NC && col0 + lane < cnt)
                 *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
-                    reinterpret_cast<const uint4 *>(st)[lane];
+                    *reinterpret_cast<const uint4 *>(st + lane * ST_PITCH);
             if (ew == 0 && lane == 0) DBG(sub, 12);
             if (p.one_release) {
                 // one release per sub-batch and step instead of one per warp (MEMBAR.GPU instances of one SM appear to
@@ -392,12 +406,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     red_release_gpu_add(ctr, EW);             // cumulative over the barrier: all the sub-batch's stores
                     DBG(sub, 13);
                 }
-                if (lane == 0) mbar_arrive(g_empty(sub, s & 1));
+                if (lane == 0) mbar_arrive(g_empty(sub, GB == 2 ? (s & 1) : 0));
             } else {
                 __syncwarp();
                 if (lane == 0) {
                     red_release_gpu_add(ctr, 1);              // publishes the warp's stores (cumulative over __syncwarp)
-                    mbar_arrive(g_empty(sub, s & 1));
+                    mbar_arrive(g_empty(sub, GB == 2 ? (s & 1) : 0));
                     if (ew == 0) DBG(sub, 13);
                 }
             }
@@ -411,15 +425,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     }
 }
 
-template <bool BF16, int SUB, int NS, int EW>
+template <bool BF16, int SUB, int NS, int EW, int GB = 2>
 int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
-    using C = Cfg<SUB, NS, EW>;
+    using C = Cfg<SUB, NS, EW, GB>;
     CUtensorMap tmY, tmG;
     if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
     if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
     const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
     const int block_cap = max_groups * C::NB;
-    auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW>;
+    auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW, GB>;
     static bool configured[64] = {};      // per device: function attributes live in the device's context
     if (!configured[h->device & 63]) {
         XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -467,6 +481,9 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
     if (variant == 1)
         return h->bf16 ? launch_cfg<true, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s)
                        : launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
+    if (variant == 4)      // four chains of 32 chunks on 24 x 4 = 96 CTAs at N = 512 (feasibility of the overlap plan)
+        return h->bf16 ? launch_cfg<true, 4, 32, 4, 1>(h, layer, y_tnc, T, N, reverse, s)
+                       : launch_cfg<false, 4, 32, 4, 1>(h, layer, y_tnc, T, N, reverse, s);
     if (variant == 3)
         return h->bf16 ? launch_cfg<true, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s)
                        : launch_cfg<false, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s);
