@@ -9,8 +9,9 @@ posteriors -> max-marginal Viterbi -> left-packed base strings.  Metric (bonito/
 input signal samples consumed per second.
 
   value   whole-job samples/s with the batch already resident in HBM (device-timed, max over ranks)
-  e2e     same metric through the host-buffer C-ABI call xb_compute_scores_host: pinned host signal in,
-          H2D + encoder + decode + D2H of packed strings inside the timed region
+  e2e     same metric through the host-buffer C-ABI calls xb_compute_scores_submit / _wait (the pipelined form of
+          xb_compute_scores_host that crf.basecall() uses): pinned host signal in, H2D + encoder + decode + D2H of packed
+          strings of every step inside the timed region, batch i+1 submitted before batch i is collected
   roofline  dominant kernel (LSTM recurrence, tensor-core bound): algorithmic FLOPs / CUDA-event time
   cpu_baseline  the oracle's restatement of the reference CPU path, timed on this box's host cores on a
           bounded sample (rank 0, N=1 only)
@@ -234,12 +235,23 @@ def main():
     h.set_profiling(False)
 
     # end to end through the host-buffer C-ABI call
-    for _ in range(2):
-        h.compute_scores_host(x_host, seq_host, lens_host)
+    # (xb_compute_scores_submit / _wait: the pipelined form of xb_compute_scores_host that basecall() uses -- batch i+1 is
+    # submitted before batch i is collected; every step still copies its input from pinned host memory and its result back)
+    seq_hosts = [seq_host, torch.empty_like(seq_host).pin_memory()]
+    lens_hosts = [lens_host, torch.empty_like(lens_host).pin_memory()]
+
+    def run_e2e(k):
+        for i in range(k):
+            if i >= 2:
+                h.compute_scores_wait(i & 1)
+            h.compute_scores_submit(i & 1, x_host, seq_hosts[i & 1], lens_hosts[i & 1])
+        for i in range(max(k - 2, 0), k):
+            h.compute_scores_wait(i & 1)
+
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        h.compute_scores_host(x_host, seq_host, lens_host)
+    run_e2e(args.steps)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.summary()

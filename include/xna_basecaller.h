@@ -169,6 +169,15 @@ int xb_preprocess_reads(xb_handle *h, const int16_t *raw, const int64_t *read_of
 int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L, int8_t *seq_host,
                            int32_t *lens_host, void *stream);
 
+/* Pipelined form of xb_compute_scores_host for a stream of batches (the reference overlaps its stages with one thread per
+ * stage, crf/basecall.py:96-119): submit() enqueues the H2D copy, encoder, decode and D2H copy of one batch into slot 0 or 1
+ * and returns; wait() blocks until that slot's seq_host / lens_host are filled.  Submit batch i+1 before waiting for batch i
+ * and the copies hide under the kernels.  A slot must be waited for before it is submitted again; the host buffers (pinned
+ * for the copies to be asynchronous) must stay valid until then. */
+int xb_compute_scores_submit(xb_handle *h, int slot, const float *signal_host, int N, int L, int8_t *seq_host,
+                             int32_t *lens_host, void *stream);
+int xb_compute_scores_wait(xb_handle *h, int slot);
+
 /* Introspection used by tests / bench: number of kernels this library launched on the handle so far. */
 int64_t xb_launch_count(const xb_handle *h);
 

@@ -223,3 +223,25 @@ def test_batch_position_independence_odd_sizes():
         seq, _, lens = h.decode(s, want_qstring=False)
         assert torch.equal(seq, seq0[idx]) and torch.equal(lens, lens0[idx]), N
     h.close()
+
+
+def test_pipelined_host_entry_points_match_the_blocking_one(enc5):
+    """xb_compute_scores_submit / _wait over five different batches in two slots == xb_compute_scores_host per batch."""
+    h, _ = enc5
+    batches = [synthetic_signal(40 + i, 3, 500)[:, 0, :].contiguous().pin_memory() for i in range(5)]
+    want = [tuple(t.clone() for t in h.compute_scores_host(b)) for b in batches]
+    seqs = [torch.empty(3, 100, dtype=torch.int8).pin_memory() for _ in range(2)]
+    lens = [torch.empty(3, dtype=torch.int32).pin_memory() for _ in range(2)]
+    got = []
+    for i, b in enumerate(batches):
+        if i >= 2:
+            h.compute_scores_wait(i & 1)
+            got.append((seqs[i & 1].clone(), lens[i & 1].clone()))
+        h.compute_scores_submit(i & 1, b, seqs[i & 1], lens[i & 1])
+    for i in (3, 4):
+        h.compute_scores_wait(i & 1)
+        got.append((seqs[i & 1].clone(), lens[i & 1].clone()))
+    assert len(got) == 5
+    for (ws, wl), (gs, gl) in zip(want, got):
+        assert torch.equal(ws, gs) and torch.equal(wl, gl)
+    assert any(int(wl.sum()) > 0 for _, wl in want)

@@ -23,7 +23,7 @@ SYMBOLS = (
     'xb_load_lstm_weights', 'xb_load_head_weights', 'xb_conv_stem_fwd',
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
-    'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_launch_count', 'xb_gemm_selftest',
+    'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_compute_scores_submit', 'xb_compute_scores_wait', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
@@ -64,6 +64,8 @@ def load():
     lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
+    lib.xb_compute_scores_submit.argtypes = [vp, ci, vp, ci, ci, vp, vp, vp]
+    lib.xb_compute_scores_wait.argtypes = [vp, ci]
     lib.xb_preprocess_reads.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_bwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp, vp, vp]
     lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
@@ -358,6 +360,15 @@ class Handle:
         self._check(self.lib.xb_preprocess_reads(self.h, _ptr(raw), _ptr(ro), _ptr(rl), _ptr(sc), _ptr(of), n, _ptr(out),
                                                  _ptr(out_len), _ptr(stats), _stream(dev)), 'xb_preprocess_reads')
         return out, out_len, stats
+
+    def compute_scores_submit(self, slot, signal_host, seq_host, lens_host):
+        """Enqueue one batch (pinned host tensors) into slot 0 / 1; results are valid after compute_scores_wait(slot)."""
+        N, L = signal_host.shape
+        self._check(self.lib.xb_compute_scores_submit(self.h, int(slot), _ptr(signal_host), N, L, _ptr(seq_host),
+                                                      _ptr(lens_host), _stream(self.device)), 'xb_compute_scores_submit')
+
+    def compute_scores_wait(self, slot):
+        self._check(self.lib.xb_compute_scores_wait(self.h, int(slot)), 'xb_compute_scores_wait')
 
     def compute_scores_host(self, signal_host, seq_host=None, lens_host=None):
         """signal_host: (N, L) fp32 CPU tensor (pinned for async copies) -> packed sequences on the host."""

@@ -68,6 +68,29 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
     }
 
 
+def _submit_scores(model, batch, slot):
+    """Pipelined half of compute_scores: stage the batch in the slot's pinned buffer and enqueue it."""
+    if not model.encoder[-1].expand_blanks or model.encoder._stem() is None:
+        raise RuntimeError('the pipelined path needs the sup@v3.3 encoder layout with expand_blanks')
+    device = next(model.parameters()).device
+    N, _, L = batch.shape
+    T = L // model.stride
+    h = model.seqdist.engine.get(device, N, T, bf16=next(model.parameters()).dtype == torch.bfloat16)
+    model.encoder.sync_weights(h)
+    staged = _pinned(model, 'signal%d' % slot, (N, L), torch.float32)
+    staged.copy_(batch[:, 0, :])
+    seq_pin, lens_pin = _pinned(model, 'seq%d' % slot, (N, T), torch.int8), _pinned(model, 'lens%d' % slot, (N,), torch.int32)
+    h.compute_scores_submit(slot, staged, seq_pin, lens_pin)
+    return h, slot, seq_pin, N, T
+
+
+def _collect_scores(h, slot, seq_pin, N, T):
+    h.compute_scores_wait(slot)
+    sequence = seq_pin.clone()
+    qstring = torch.where(sequence != 0, torch.tensor(ord('O'), dtype=torch.int8), torch.tensor(0, dtype=torch.int8))
+    return {'qstring': qstring, 'sequence': sequence, 'moves': np.zeros((N, T), dtype=bool)}
+
+
 def to_str(x):
     """koi.decode.to_str as used by the reference: drop zeros, bytes -> ascii."""
     x = np.asarray(x)
@@ -96,8 +119,22 @@ def basecall(model, reads, chunksize=4000, overlap=100, batchsize=32, reverse=Fa
             yield (read, 0, len(read.signal)), chunk(torch.from_numpy(read.signal), chunksize, overlap)
 
     def scored(batches):
-        for keys, batch in batches:
-            yield keys, compute_scores(model, batch, reverse=reverse)
+        # one batch ahead on the GPU: batch i+1 is submitted (xb_compute_scores_submit: H2D, encoder, decode, D2H on their own
+        # streams) before the results of batch i are collected, so the copies hide under the kernels
+        in_flight = None
+        for i, (keys, batch) in enumerate(batches):
+            if reverse or batch.device.type != 'cpu':
+                if in_flight is not None:
+                    yield in_flight[0], _collect_scores(*in_flight[1:])
+                    in_flight = None
+                yield keys, compute_scores(model, batch, reverse=reverse)
+                continue
+            job = (keys,) + _submit_scores(model, batch, i & 1)
+            if in_flight is not None:
+                yield in_flight[0], _collect_scores(*in_flight[1:])
+            in_flight = job
+        if in_flight is not None:
+            yield in_flight[0], _collect_scores(*in_flight[1:])
 
     def stitched(per_read):
         for (read, start, end), parts in per_read:

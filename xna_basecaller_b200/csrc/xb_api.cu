@@ -221,6 +221,13 @@ int xb_destroy(xb_handle *h) {
                     h->alpha, h->bmax, h->lp, h->logz, h->ctc_ws, h->lstm_counters};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (void *p : {(void *)h->signal_dev2, (void *)h->seq_dev2, (void *)h->lens_dev2})
+        if (p) cudaFree(p);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    for (int i = 0; i < 2; i++)
+        for (cudaEvent_t e : {h->ev_h2d[i], h->ev_enc[i], h->ev_dec[i], h->ev_done[i]})
+            if (e) cudaEventDestroy(e);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto &l : h->lstm) {
@@ -542,6 +549,68 @@ int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L,
     XB_CUDA(h, cudaMemcpyAsync(seq_host, h->seq_dev, (size_t)N * T, cudaMemcpyDeviceToHost, s));
     XB_CUDA(h, cudaMemcpyAsync(lens_host, h->lens_dev, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     XB_CUDA(h, cudaStreamSynchronize(s));
+    return XB_OK;
+}
+
+// Pipelined form of xb_compute_scores_host: two slots; submit() enqueues H2D (own copy stream), encoder + decode (the
+// caller's stream) and D2H (second copy stream) of one batch and returns, wait() blocks until the slot's results are in
+// the host buffers.  With batch i+1 submitted before batch i is awaited, the copies of one batch hide under the kernels
+// of the other.  A slot must be awaited before it is submitted again; host buffers must stay valid until then.
+static int pipeline_init(xb_handle *h) {
+    if (h->h2d_stream) return XB_OK;
+    const size_t TN = (size_t)h->max_T * h->max_N;
+    XB_CUDA(h, cudaMalloc(&h->signal_dev2, TN * XB_STRIDE * sizeof(float)));
+    XB_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->seq_dev2), TN));
+    XB_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->lens_dev2), (size_t)h->max_N * sizeof(int32_t)));
+    XB_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    XB_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        XB_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        XB_CUDA(h, cudaEventCreateWithFlags(&h->ev_enc[i], cudaEventDisableTiming));
+        XB_CUDA(h, cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming));
+        XB_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    return XB_OK;
+}
+
+int xb_compute_scores_submit(xb_handle *h, int slot, const float *signal_host, int N, int L, int8_t *seq_host,
+                             int32_t *lens_host, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, slot == 0 || slot == 1, "slot must be 0 or 1");
+    XB_REQUIRE(h, signal_host && seq_host && lens_host, "NULL buffer");
+    XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
+    const int T = L / XB_STRIDE;
+    if (int rc = check_tn(h, T, N)) return rc;
+    if (!h->signal_dev) return xb_fail(h, XB_ERR_STATE, "handle was created without the encoder");
+    if (int rc = pipeline_init(h)) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    void *sig = slot ? h->signal_dev2 : h->signal_dev;
+    int8_t *seq = slot ? h->seq_dev2 : h->seq_dev;
+    int32_t *lens = slot ? h->lens_dev2 : h->lens_dev;
+    if (h->slot_used[slot]) {       // the slot's previous batch: its signal has been consumed, its results have left
+        XB_CUDA(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_enc[slot], 0));
+        XB_CUDA(h, cudaStreamWaitEvent(s, h->ev_done[slot], 0));
+    }
+    XB_CUDA(h, cudaMemcpyAsync(sig, signal_host, (size_t)N * L * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    XB_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->h2d_stream));
+    XB_CUDA(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if (int rc = xb_encoder_fwd(h, sig, XB_SIG_F32, N, L, h->scores, stream)) return rc;
+    XB_CUDA(h, cudaEventRecord(h->ev_enc[slot], s));
+    if (int rc = xb_crf_decode(h, h->scores, T, N, seq, nullptr, lens, nullptr, nullptr, stream)) return rc;
+    XB_CUDA(h, cudaEventRecord(h->ev_dec[slot], s));
+    XB_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_dec[slot], 0));
+    XB_CUDA(h, cudaMemcpyAsync(seq_host, seq, (size_t)N * T, cudaMemcpyDeviceToHost, h->d2h_stream));
+    XB_CUDA(h, cudaMemcpyAsync(lens_host, lens, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    XB_CUDA(h, cudaEventRecord(h->ev_done[slot], h->d2h_stream));
+    h->slot_used[slot] = true;
+    return XB_OK;
+}
+
+int xb_compute_scores_wait(xb_handle *h, int slot) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, (slot == 0 || slot == 1) && h->slot_used[slot], "slot %d has nothing in flight", slot);
+    XB_CUDA(h, cudaSetDevice(h->device));
+    XB_CUDA(h, cudaEventSynchronize(h->ev_done[slot]));
     return XB_OK;
 }
 

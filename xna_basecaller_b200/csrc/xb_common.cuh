@@ -67,6 +67,14 @@ struct xb_handle {
     void *signal_dev = nullptr;  // (max_N, max_T*5) fp32 staging for the host entry points
     int8_t *seq_dev = nullptr;   // (max_N, max_T)
     int32_t *lens_dev = nullptr; // (max_N)
+    // second slot + copy streams of the pipelined host entry points (xb_compute_scores_submit / _wait), created on first use
+    void *signal_dev2 = nullptr;
+    int8_t *seq_dev2 = nullptr;
+    int32_t *lens_dev2 = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_enc[2] = {nullptr, nullptr}, ev_dec[2] = {nullptr, nullptr},
+                ev_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
 
     // decode workspace
     float *alpha = nullptr;      // (max_T+1, max_N, C)
