@@ -41,8 +41,17 @@ template <int NPEND> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(NPEND));
 }
 
+// One score row global -> shared in 8-byte cp.async pieces (rows are only 8-byte aligned: S * 4 = 3000 B for n_base 5).
+// Fully unrolled on one shared and one global base address with immediate offsets: the rolled loop spent ~24 instructions
+// per piece on address arithmetic -- a quarter of the alpha sweep's instruction count.
 template <int NFLOATS, int NT> __device__ __forceinline__ void copy_row(float *dst, const float *src) {
-    for (int i = threadIdx.x; i < NFLOATS / 2; i += NT) cp_async8(dst + 2 * i, src + 2 * i);
+    constexpr int NCOPY = NFLOATS / 2, ROUNDS = (NCOPY + NT - 1) / NT;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + threadIdx.x * 8u;
+    const char *g = reinterpret_cast<const char *>(src) + threadIdx.x * 8u;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; k++)
+        if ((k + 1) * NT <= NCOPY || k * NT + (int)threadIdx.x < NCOPY)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + (uint32_t)(k * NT * 8)), "l"(g + k * NT * 8));
 }
 
 // warp maximum with one integer REDUX on an order-preserving key (max is exact, so any evaluation order gives the same
@@ -312,9 +321,12 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
         }
         __syncthreads();                                                        // B3
         {
-            float2 *dst = reinterpret_cast<float2 *>(lp_out + ((size_t)t * N + n) * S);
-            const float2 *srcv = reinterpret_cast<const float2 *>(LP);
-            for (int j = c; j < S / 2; j += NT) dst[j] = srcv[j];
+            float2 *dst = reinterpret_cast<float2 *>(lp_out + ((size_t)t * N + n) * S) + c;
+            const float2 *srcv = reinterpret_cast<const float2 *>(LP) + c;
+            constexpr int NPAIR = S / 2, ROUNDS = (NPAIR + NT - 1) / NT;
+#pragma unroll
+            for (int k = 0; k < ROUNDS; k++)                 // unrolled on one base address each, immediate offsets
+                if ((k + 1) * NT <= NPAIR || k * NT + c < NPAIR) dst[k * NT] = srcv[k * NT];
         }
         if (act) {
             float m = XB_ADD(LP[c * NZ], m1[c]);
