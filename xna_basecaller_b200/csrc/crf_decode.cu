@@ -108,12 +108,17 @@ crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restri
 #pragma unroll
     for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
 
+    // running pointers instead of per-step 64-bit index arithmetic: next row to fetch, next alpha row to write
+    const float *fetch = base + (size_t)(D - 1) * row;
+    float *aout = alpha_out ? alpha_out + ((size_t)N + n) * C + c : nullptr;
+    const size_t arow = (size_t)N * C;
     for (int t = 0; t < T; t++) {
         cp_async_wait<D - 2>();
         __syncthreads();
         {
             int r = t + D - 1;
-            if (r < T) copy_row<S, NT>(ring + (r % D) * S, base + (size_t)r * row);
+            if (r < T) copy_row<S, NT>(ring + (r % D) * S, fetch);
+            fetch += row;
             cp_async_commit();
         }
         const float *M = ring + (t % D) * S + c * NZ;
@@ -128,8 +133,9 @@ crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restri
             }
             float v = lse_exact<NZ>(x, m);
             an[c] = v;
-            if (alpha_out) alpha_out[((size_t)(t + 1) * N + n) * C + c] = v;
+            if (aout) *aout = v;
         }
+        if (aout) aout += arow;
     }
     __syncthreads();
     if (logz_out) {
@@ -246,6 +252,9 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
     for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
     const int kk = act ? 1 + c / L::NP : 1, cb = act ? (c % L::NP) * NB : 0;
 
+    // running pointers (rows are visited in descending t) instead of per-step 64-bit index arithmetic
+    const float *fetchM = base + (size_t)(T - D) * row;          // row T-1-r for r = D-1
+    const float *fetchA = abase + (size_t)(T - D) * arow + c;
     for (int i = 0; i < T; i++) {
         const int t = T - 1 - i;
         cp_async_wait<D - 2>();
@@ -253,9 +262,11 @@ crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ 
         {
             int r = i + D - 1;
             if (r < T) {
-                copy_row<S, NT>(ringM + (r % D) * S, base + (size_t)(T - 1 - r) * row);
-                if (act) cp_async4(ringA + (r % D) * NT + c, abase + (size_t)(T - 1 - r) * arow + c);
+                copy_row<S, NT>(ringM + (r % D) * S, fetchM);
+                if (act) cp_async4(ringA + (r % D) * NT + c, fetchA);
             }
+            fetchM -= row;
+            fetchA -= arow;
             cp_async_commit();
         }
         const float *M = ringM + (i % D) * S;
@@ -379,15 +390,19 @@ crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ b
 #pragma unroll
     for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
 
+    const float *fetchM = base + (size_t)(D - 1) * row;          // running pointers: row r = t + D - 1, Max-beta row r + 1
+    const float *fetchB = bbase + (size_t)D * brow + c;
     for (int t = 0; t < T; t++) {
         cp_async_wait<D - 2>();
         __syncthreads();
         {
             int r = t + D - 1;
             if (r < T) {
-                copy_row<S, NT>(ring + (r % D) * S, base + (size_t)r * row);
-                if (act) cp_async4(ringB + (r % D) * NT + c, bbase + (size_t)(r + 1) * brow + c);
+                copy_row<S, NT>(ring + (r % D) * S, fetchM);
+                if (act) cp_async4(ringB + (r % D) * NT + c, fetchB);
             }
+            fetchM += row;
+            fetchB += brow;
             cp_async_commit();
         }
         if (c == 0 && t > 0) {           // finish step t-1: reduce the per-warp candidates
