@@ -389,14 +389,16 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                                    : const_cast<uint16_t *>(Gs) + col0 * 128 + q * 32;
             if (GB == 1) __syncwarp();                           // every lane has taken its G values
 #pragma unroll
+            // explicit shared-memory instructions: behind the casts the compiler falls back to generic loads / stores
+            const uint32_t st_s = smem_u32(st);
             for (int i = 0; i < CELLS; i++) {
                 typename X::T hv = X::from(hout[i]);
-                st[(8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul] = *reinterpret_cast<uint16_t *>(&hv);
+                sts_u16(st_s + 2u * ((8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul), *reinterpret_cast<uint16_t *>(&hv));
             }
             __syncwarp();
             if (lane < NC && col0 + lane < cnt)
                 *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
-                    *reinterpret_cast<const uint4 *>(st + lane * ST_PITCH);
+                    lds_v4(st_s + 2u * (lane * ST_PITCH));
             if (ew == 0 && lane == 0) DBG(sub, 12);
             if (p.one_release) {
                 // one release per sub-batch and step instead of one per warp (MEMBAR.GPU instances of one SM appear to

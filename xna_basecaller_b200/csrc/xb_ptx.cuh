@@ -50,6 +50,9 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
 __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
