@@ -18,8 +18,11 @@
  *   - device pointers unless the parameter name ends in _host.
  *   - T = L / stride (stride 5), C = n_base^state_len states, NZ = n_base+1 edges per state,
  *     scores are (T, N, C*NZ) fp32 in the reference's layout (nn.py:122-129).
- *   - the 16-bit activation / weight type is fp16 (what the reference itself uses on GPU,
- *     util.py:360-363) unless XB_FLAG_BF16 is given; accumulation and LSTM cell state are fp32.
+ *   - activations are fp16 and so are the weights (what the reference itself uses on GPU,
+ *     util.py:360-363); XB_FLAG_BF16 rounds the WEIGHTS to bfloat16 (a bf16 checkpoint's own values,
+ *     held exactly in fp16 storage) and multiplies them with fp16 activations -- h, the hoisted input
+ *     projection and the stem output are bounded, so the 11-bit mantissa of fp16 is the better 16-bit
+ *     format for them.  Accumulation, LSTM cell state and scores are fp32.
  */
 #ifndef XNA_BASECALLER_H
 #define XNA_BASECALLER_H
@@ -44,9 +47,9 @@ enum xb_status {
 };
 
 enum xb_flags {
-    XB_FLAG_BF16 = 1,            /* 16-bit type is bfloat16 instead of float16                 */
-    XB_FLAG_NO_ENCODER = 2,      /* decode-only handle: no encoder workspace is allocated      */
-    XB_FLAG_LSTM_STEPWISE = 4    /* force the one-launch-per-step LSTM (debug / comparison)   */
+    XB_FLAG_BF16 = 1,            /* weights rounded to bfloat16 (activations stay float16)     */
+    XB_FLAG_NO_ENCODER = 2       /* decode-only handle: no encoder workspace is allocated      */
+    /* (4 was the one-launch-per-step LSTM of round 1; it exists only in -DXB_EXPERIMENTS builds) */
 };
 
 enum xb_signal_dtype { XB_SIG_F32 = 0, XB_SIG_F16 = 1, XB_SIG_I16 = 2 };
@@ -190,7 +193,7 @@ int64_t xb_launch_count(const xb_handle *h);
 int xb_set_profiling(xb_handle *h, int on);
 int xb_stage_times(xb_handle *h, float *ms, int *spans);
 
-/* Standalone tensor-core GEMM self-test hook: D (M,N) fp32 = A (M,K) x B (N,K)^T, 16-bit operands. */
+/* Standalone tensor-core GEMM self-test hook: D (M,N) fp32 = A (M,K) x B (N,K)^T, fp16 operands. */
 int xb_gemm_selftest(xb_handle *h, const void *A, const void *B, float *D, int M, int N, int K,
                      void *stream);
 

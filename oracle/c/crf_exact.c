@@ -238,6 +238,145 @@ int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len,
     return xbo_crf_decode_range(scores, T, N, 0, N, n_base, state_len, post, lp_out, labels);
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Linear-domain (scaled) decode: the arithmetic contract of the CUDA kernels crf_lin_alpha / crf_lin_backward /
+ * crf_lin_viterbi in xna_basecaller_b200/csrc/crf_decode_lin.cu.  Same reference semantics as xbo_crf_decode
+ * (bonito/crf/model.py:41-46, 92-95, 215-218: Log-semiring posteriors, + 1e-8, Max-semiring marginals of their logs,
+ * arg-max % NZ), restated without per-state logarithms:
+ *   E = exp(M) per edge (xb_expf; scores clamped to [-80, 80]);  Log semiring -> sums of products;  the Max semiring
+ *   over log(p + 1e-8) -> max of products of (p + 1e-8) (log is monotone, so the arg-max is the same in exact arithmetic).
+ *   Every state vector is rescaled by a power of two taken from its own maximum (exact), so nothing over/underflows:
+ *     scale(mx) = 2^(127 - biased_exponent(mx))  (1 if mx is zero, subnormal, inf or nan);  v_hat = v * scale(max v).
+ *   forward:   u_{t+1}[c] = fma-chain over k (k order) of E_t[c,k] * a_hat_t[src(c,k)],  a_hat_0 = 1
+ *   backward:  w_e = E_t[e] * b_hat_{t+1}[dst(e)] over the edges leaving s (stay, then moves j = 0..n-1);
+ *              u_t[s] = ((w_0 + w_1) + ...);  b_hat_T = 1
+ *   posterior: x_e = a_hat_t[s] * w_e;  xs_s = ((x_0 + x_1) + ...);  tot_t = tree_sum over states (as above);
+ *              p_e = x_e * (1 / tot_t);  P_e = p_e + 1e-8
+ *   Max-beta:  um_t[s] = max_e P_e * bm_hat_{t+1}[dst(e)],  bm_hat_T = 1
+ *   Max-alpha: v_k = P_t[c,k] * am_hat_t[src(c,k)];  um_{t+1}[c] = max_k v_k,  am_hat_0 = 1
+ *   label_t  = (arg-max over the flat edge index c*NZ+k of v_k * bm_hat_{t+1}[c], first index on ties) % NZ
+ * lin_input != 0: `scores` already holds E (what the fused head writes). */
+static inline float pow2_scale(float mx) {
+    uint32_t e = (XB_F2U(mx) >> 23) & 0xffu;
+    if (e == 0u || e == 255u || (XB_F2U(mx) >> 31)) return 1.0f;
+    return XB_U2F((254u - e) << 23);
+}
+static inline float vec_max(const float *v, int C) {
+    float m = v[0];
+    for (int c = 1; c < C; c++) m = v[c] > m ? v[c] : m;
+    return m;
+}
+static inline float edge_E(const float *row, size_t i, int lin_input) {
+    if (lin_input) return row[i];
+    float m = row[i];
+    m = m < -80.0f ? -80.0f : (m > 80.0f ? 80.0f : m);
+    return xb_expf(m);
+}
+
+int xbo_crf_decode_lin_range(const float *scores, int lin_input, int T, int N, int n_begin, int n_end, int n_base,
+                             int state_len, float *post, int8_t *labels) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    const int C = L.C, NZ = L.NZ;
+    size_t S = (size_t)C * NZ;
+    float *ah = (float *)malloc((size_t)(T + 1) * C * sizeof(float));     /* a_hat */
+    float *bh = (float *)malloc((size_t)(T + 1) * C * sizeof(float));     /* b_hat */
+    float *bm = (float *)malloc((size_t)(T + 1) * C * sizeof(float));     /* bm_hat */
+    float *tot = (float *)malloc((size_t)T * sizeof(float));
+    float *E = (float *)malloc(S * sizeof(float));
+    if (!ah || !bh || !bm || !tot || !E) return -2;
+    for (int n = n_begin; n < n_end; n++) {
+        float u[MAXC], xs[MAXC];
+        /* forward */
+        for (int c = 0; c < C; c++) ah[c] = 1.0f;
+        for (int t = 0; t < T; t++) {
+            const float *row = scores + ((size_t)t * N + n) * S, *a = ah + (size_t)t * C;
+            for (int c = 0; c < C; c++) {
+                float acc = XB_MUL(edge_E(row, (size_t)c * NZ, lin_input), a[c]);
+                for (int k = 1; k < NZ; k++)
+                    acc = XB_FMA(edge_E(row, (size_t)c * NZ + k, lin_input), a[src_state(&L, c, k)], acc);
+                u[c] = acc;
+            }
+            float sc = pow2_scale(vec_max(u, C));
+            for (int c = 0; c < C; c++) ah[(size_t)(t + 1) * C + c] = XB_MUL(u[c], sc);
+        }
+        /* backward: b_hat, posteriors' normaliser, Max-beta over P */
+        for (int c = 0; c < C; c++) { bh[(size_t)T * C + c] = 1.0f; bm[(size_t)T * C + c] = 1.0f; }
+        for (int t = T - 1; t >= 0; t--) {
+            const float *row = scores + ((size_t)t * N + n) * S;
+            const float *a = ah + (size_t)t * C, *b1 = bh + (size_t)(t + 1) * C, *m1 = bm + (size_t)(t + 1) * C;
+            for (size_t i = 0; i < S; i++) E[i] = edge_E(row, i, lin_input);
+            float um[MAXC];
+            /* first the sums (they define tot), then the Max recursion which needs 1 / tot */
+            for (int s = 0; s < C; s++) {
+                int kk = 1 + s / L.n_pow, base = (s % L.n_pow) * L.n;
+                float w = XB_MUL(E[(size_t)s * NZ], b1[s]);
+                float x = XB_MUL(a[s], w);
+                float su = w, sx = x;
+                for (int j = 0; j < L.n; j++) {
+                    w = XB_MUL(E[(size_t)(base + j) * NZ + kk], b1[base + j]);
+                    x = XB_MUL(a[s], w);
+                    su = XB_ADD(su, w);
+                    sx = XB_ADD(sx, x);
+                }
+                u[s] = su;
+                xs[s] = sx;
+            }
+            tot[t] = tree_sum(xs, C);
+            float inv = XB_RCP(tot[t]);
+            for (int s = 0; s < C; s++) {
+                int kk = 1 + s / L.n_pow, base = (s % L.n_pow) * L.n;
+                float x = XB_MUL(a[s], XB_MUL(E[(size_t)s * NZ], b1[s]));
+                float p = XB_MUL(x, inv);
+                if (post) post[((size_t)t * N + n) * S + (size_t)s * NZ] = p;
+                float best = XB_MUL(XB_ADD(p, XB_POST_EPS), m1[s]);
+                for (int j = 0; j < L.n; j++) {
+                    size_t e = (size_t)(base + j) * NZ + kk;
+                    x = XB_MUL(a[s], XB_MUL(E[e], b1[base + j]));
+                    p = XB_MUL(x, inv);
+                    if (post) post[((size_t)t * N + n) * S + e] = p;
+                    float v = XB_MUL(XB_ADD(p, XB_POST_EPS), m1[base + j]);
+                    best = v > best ? v : best;
+                }
+                um[s] = best;
+            }
+            float sb = pow2_scale(vec_max(u, C)), sm = pow2_scale(vec_max(um, C));
+            for (int s = 0; s < C; s++) {
+                bh[(size_t)t * C + s] = XB_MUL(u[s], sb);
+                bm[(size_t)t * C + s] = XB_MUL(um[s], sm);
+            }
+        }
+        /* forward, Max semiring over P, arg-max */
+        float am[2][MAXC];
+        for (int c = 0; c < C; c++) am[0][c] = 1.0f;
+        for (int t = 0; t < T; t++) {
+            const float *row = scores + ((size_t)t * N + n) * S;
+            const float *a = ah + (size_t)t * C, *b1 = bh + (size_t)(t + 1) * C, *m1 = bm + (size_t)(t + 1) * C;
+            const float *ac = am[t & 1];
+            float inv = XB_RCP(tot[t]);
+            float best = 0.0f; int besti = -1;
+            for (int c = 0; c < C; c++) {
+                float m = 0.0f;
+                for (int k = 0; k < NZ; k++) {
+                    int sidx = src_state(&L, c, k);
+                    float w = XB_MUL(edge_E(row, (size_t)c * NZ + k, lin_input), b1[c]);
+                    float x = XB_MUL(a[sidx], w);
+                    float P = XB_ADD(XB_MUL(x, inv), XB_POST_EPS);
+                    float v = XB_MUL(P, ac[sidx]);
+                    m = (k == 0 || v > m) ? v : m;
+                    float cand = XB_MUL(v, m1[c]);
+                    if (besti < 0 || cand > best) { best = cand; besti = c * NZ + k; }
+                }
+                u[c] = m;
+            }
+            float sc = pow2_scale(vec_max(u, C));
+            for (int c = 0; c < C; c++) am[(t + 1) & 1][c] = XB_MUL(u[c], sc);
+            labels[(size_t)n * T + t] = (int8_t)(besti % NZ);
+        }
+    }
+    free(ah); free(bh); free(bm); free(tot); free(E);
+    return 0;
+}
+
 int xbo_crf_posteriors(const float *scores, int T, int N, int n_base, int state_len, float *post) {
     int8_t *lab = (int8_t *)malloc((size_t)N * T);
     if (!lab) return -2;

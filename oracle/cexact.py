@@ -125,6 +125,26 @@ def crf_decode_threads(scores, n_base, state_len=3, threads=1):
     return labels
 
 
+def crf_decode_lin(scores, n_base, state_len=3, want_post=False, lin_input=False, threads=1):
+    """Linear-domain (scaled) decode, the contract of the CUDA decode kernels: labels (N,T) int8 [, posteriors].
+    lin_input: `scores` already holds exp(scores) (what the fused head hands to the decode)."""
+    from concurrent.futures import ThreadPoolExecutor
+    s = _f32(scores)
+    T, N, _ = s.shape
+    labels = np.empty((N, T), dtype=np.int8)
+    post = np.empty_like(s) if want_post else None
+    threads = max(1, min(threads, N))
+    bounds = [(N * i // threads, N * (i + 1) // threads) for i in range(threads)]
+    fn = lib().xbo_crf_decode_lin_range
+
+    def work(b):
+        return fn(_p(s), int(lin_input), T, N, b[0], b[1], n_base, state_len, _p(post) if want_post else None, _p(labels))
+
+    with ThreadPoolExecutor(threads) as ex:
+        assert all(rc == 0 for rc in ex.map(work, bounds))
+    return (labels, post) if want_post else labels
+
+
 def crf_viterbi(scores, n_base, state_len=3):
     s = _f32(scores)
     T, N, _ = s.shape

@@ -3,7 +3,8 @@ golden vectors produced by the reference's own bonito.nn / bonito.crf.model code
 
 Tolerance (BASELINE.json north_star): max abs error <= 1e-2 on the CRF scores (range +-5) with 16-bit
 tensor-core operands against the fp32 reference.  The 16-bit type is fp16 by default -- what the reference
-itself runs on GPU (bonito/util.py:360-363); bf16 is an option and is checked against a looser bound."""
+itself runs on GPU (bonito/util.py:360-363); the bf16 option rounds the weights to bfloat16 and keeps fp16 activations
+(tests/precision_attribution.py shows why), and meets the same bound."""
 import numpy as np
 import pytest
 import torch
@@ -15,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 SCORE_TOL_F16 = 1e-2          # reference-scale weights (unit gains, like the reference's own init)
 SCORE_TOL_F16_AMPLIFIED = 6e-2  # test weights with a 12x head gain: fp16 weight rounding alone gives ~3e-2
-SCORE_TOL_BF16 = 5e-2           # bf16 operands at reference scale (8 mantissa bits: misses the 1e-2 bar)
+SCORE_TOL_BF16 = 1e-2           # bf16-rounded weights x fp16 activations at reference scale
 
 
 @pytest.fixture(scope='module')
@@ -28,15 +29,13 @@ def enc5():
     h.close()
 
 
-@pytest.mark.parametrize('bf16', [False, True])
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 768), (1000, 640, 320), (77, 128, 128)])
-def test_gemm_selftest(bf16, M, N, K):
+def test_gemm_selftest(M, N, K):
     from xna_basecaller_b200._lib import Handle
-    h = Handle(ALPHABETS[5], 3, max_N=4, max_T=8, bf16=bf16, encoder=False)
-    dt = torch.bfloat16 if bf16 else torch.float16
+    h = Handle(ALPHABETS[5], 3, max_N=4, max_T=8, encoder=False)
     g = torch.Generator(device='cuda').manual_seed(M + N + K)
-    A = torch.randn(M, K, device='cuda', generator=g).to(dt)
-    B = torch.randn(N, K, device='cuda', generator=g).to(dt)
+    A = torch.randn(M, K, device='cuda', generator=g).half()
+    B = torch.randn(N, K, device='cuda', generator=g).half()
     D = h.gemm_selftest(A, B)
     ref = A.float() @ B.float().t()
     err = (D - ref).abs().max().item()
@@ -67,12 +66,11 @@ def test_lstm_layer(enc5, reverse):
     assert (got - ref).abs().max().item() < 4e-3
 
 
-@pytest.mark.parametrize('stepwise', [False, True])
 @pytest.mark.parametrize('N,T', [(100, 24), (200, 17), (577, 6)])
-def test_lstm_layer_multi_group(stepwise, N, T):
+def test_lstm_layer_multi_group(N, T):
     """Several batch groups per launch (96 chunks each), uneven last group, and more than one launch (N > 576)."""
     from xna_basecaller_b200._lib import Handle
-    h = Handle(ALPHABETS[5], 3, max_N=N, max_T=T, lstm_stepwise=stepwise)
+    h = Handle(ALPHABETS[5], 3, max_N=N, max_T=T)
     sd = bo.reference_state_dict(n_base=5, seed=11)
     h.load_weights(sd)
     g = torch.Generator().manual_seed(N + T)

@@ -13,7 +13,6 @@ LIB_PATH = os.path.join(_HERE, 'libxna_b200.so')
 
 XB_FLAG_BF16 = 1
 XB_FLAG_NO_ENCODER = 2
-XB_FLAG_LSTM_STEPWISE = 4
 XB_SIG_F32, XB_SIG_F16, XB_SIG_I16 = 0, 1, 2
 NUM_WEIGHTS = 28
 
@@ -95,8 +94,7 @@ class Handle:
     """One xb_handle: a device, an alphabet, capacity (max_N chunks x max_T steps) and, after
     load_weights(), the repacked encoder weights."""
 
-    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True,
-                 lstm_stepwise=False):
+    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True):
         if not torch.cuda.is_available():
             raise RuntimeError('xna_basecaller_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = load()
@@ -108,9 +106,8 @@ class Handle:
         self.max_N, self.max_T = max_N, max_T
         self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
         self.bf16 = bf16
-        self.dtype16 = torch.bfloat16 if bf16 else torch.float16
-        flags = ((XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
-                 | (XB_FLAG_LSTM_STEPWISE if lstm_stepwise else 0))
+        self.dtype16 = torch.float16        # activations are fp16 in both modes; bf16 rounds the WEIGHTS to bfloat16
+        flags = (XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
         h = ctypes.c_void_p()
         rc = self.lib.xb_create(ctypes.byref(h), self.device.index or 0, max_N, max_T, self.n_base, state_len,
                                 self.alphabet.encode(), flags)

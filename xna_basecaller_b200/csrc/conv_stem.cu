@@ -104,18 +104,10 @@ int launch(xb_handle *h, const void *signal, int N, int L, cudaStream_t s) {
 
 // signal (N, L) -> h->c2 = im2col rows (N*T, 320) 16-bit
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s) {
-    if (h->bf16) {
-        switch (sig_dtype) {
-            case XB_SIG_F32: return launch<true, float>(h, signal, N, L, s);
-            case XB_SIG_F16: return launch<true, __half>(h, signal, N, L, s);
-            case XB_SIG_I16: return launch<true, int16_t>(h, signal, N, L, s);
-        }
-    } else {
-        switch (sig_dtype) {
-            case XB_SIG_F32: return launch<false, float>(h, signal, N, L, s);
-            case XB_SIG_F16: return launch<false, __half>(h, signal, N, L, s);
-            case XB_SIG_I16: return launch<false, int16_t>(h, signal, N, L, s);
-        }
+    switch (sig_dtype) {        // activations are fp16 in both weight modes
+        case XB_SIG_F32: return launch<false, float>(h, signal, N, L, s);
+        case XB_SIG_F16: return launch<false, __half>(h, signal, N, L, s);
+        case XB_SIG_I16: return launch<false, int16_t>(h, signal, N, L, s);
     }
     return xb_fail(h, XB_ERR_ARG, "unknown signal dtype %d", sig_dtype);
 }

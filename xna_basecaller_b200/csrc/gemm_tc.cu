@@ -299,7 +299,7 @@ int xb_make_tmap_2d_box(xb_handle *h, CUtensorMap *out, const void *base, uint64
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
-        out, h->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims,
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16 /* 16-bit payload; the element type only matters for OOB fill */, 2, const_cast<void *>(base), dims,
         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -321,7 +321,7 @@ int xb_make_tmap_hview(xb_handle *h, CUtensorMap *out, const void *base, uint64_
     cuuint32_t box[3] = {64, box_rows, box_kblocks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
-        out, h->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return xb_fail(h, XB_ERR_CUDA, "cuTensorMapEncodeTiled (3-D h view) failed with CUresult %d", (int)r);
@@ -348,13 +348,15 @@ int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensor
     if (p.K % BK != 0) return xb_fail(h, XB_ERR_ARG, "GEMM K=%d is not a multiple of %d", p.K, BK);
 #define XB_EPI_CASE(E)                                                                       \
     case E:                                                                                  \
-        return h->bf16 ? launch_one<true, E>(h, tmA, tmB, p, p.M, s) : launch_one<false, E>(h, tmA, tmB, p, p.M, s);
+        return launch_one<false, E>(h, tmA, tmB, p, p.M, s);      /* fp16 operands in both weight modes (xb_api.cu repack) */
     switch (epi) {
         XB_EPI_CASE(EPI_F32)
         XB_EPI_CASE(EPI_CONV3)
+#ifdef XB_EXPERIMENTS      // the tile-GEMM forms of the input projection, the head and the step-wise LSTM (cross-check builds only)
         XB_EPI_CASE(EPI_INPROJ)
         XB_EPI_CASE(EPI_HEAD)
         XB_EPI_CASE(EPI_LSTM)
+#endif
     }
 #undef XB_EPI_CASE
     return xb_fail(h, XB_ERR_ARG, "unknown epilogue %d", epi);

@@ -22,7 +22,8 @@
 //
 // Warp roles (256 threads; 384 for IP_SCORES): warp 0 TMA producer, warp 1 MMA issuer (+ tcgen05.cp of the x block),
 // warp 2 TMEM allocator, warps 4..7 (and 8..11) run the epilogues (warp % 4 = TMEM lane quarter).  XB_INPROJ_REGLOAD=1
-// selects the earlier x path (epilogue warps load the rows, transpose them through staging rows, tcgen05.st).
+// selects the earlier x path (epilogue warps load the rows, transpose them through staging rows, tcgen05.st) in builds with
+// -DXB_EXPERIMENTS; the product library reads no environment variables.
 #include <stdlib.h>
 
 #include "xb_common.cuh"
@@ -33,6 +34,12 @@
 using namespace xbptx;
 
 namespace {
+
+#ifdef XB_EXPERIMENTS
+#define IP_CLK() clock64()       // stall accounting of the MMA thread (XB_INPROJ_DEBUG)
+#else
+#define IP_CLK() 0ll
+#endif
 
 constexpr int BM = 128, BNI = 64, BK = 64;
 constexpr int KB = XB_FEATURES / BK;                 // 12 K blocks
@@ -172,7 +179,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
         const bool dbg = p.dbg && blockIdx.x == 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tit++) {
             if (XCP) {
-                tt = clock64();
+                tt = IP_CLK();
                 for (int xs = 0; xs < KB / 2; xs++, it++) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
@@ -187,28 +194,28 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                     }
                     __syncwarp();
                 }
-                st_a += clock64() - tt;
+                st_a += IP_CLK() - tt;
             }
             for (int nt = 0; nt < NT; nt++, nit++) {
                 const int buf = nit & 1;
-                tt = clock64();
+                tt = IP_CLK();
                 mbar_wait(&acc_empty[buf], ((nit >> 1) & 1) ^ 1);
                 tc_fence_after();
-                st_acc += clock64() - tt;
+                st_acc += IP_CLK() - tt;
                 const uint32_t d = tmem_base + A_COLS + buf * BNI;
                 for (int ks = 0; ks < SPT; ks++, it++) {
                     const int s = it % STAGES;
-                    tt = clock64();
+                    tt = IP_CLK();
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     tc_fence_after();
-                    st_full += clock64() - tt;
+                    st_full += IP_CLK() - tt;
                     if (!XCP && nt == 0) {                     // first N tile: the x block arrives K-block group by group
-                        tt = clock64();
+                        tt = IP_CLK();
                         mbar_wait(&a_ready[ks], tit & 1);
                         tc_fence_after();
-                        st_a += clock64() - tt;
+                        st_a += IP_CLK() - tt;
                     }
-                    tt = clock64();
+                    tt = IP_CLK();
                     if (elect_one()) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES));
                         const uint32_t a0 = tmem_base + ks * KPS * (BK / 2);
@@ -222,7 +229,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                         if (ks == SPT - 1) mma_commit(&acc_full[buf]);
                     }
                     __syncwarp();
-                    st_issue += clock64() - tt;
+                    st_issue += IP_CLK() - tt;
                 }
             }
         }
@@ -281,7 +288,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                 constexpr int RS = 81;
                 float *S = reinterpret_cast<float *>(stg);
                 const bool dbg = p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0;
-                const long long te0 = clock64();
+                const long long te0 = IP_CLK();
                 const int col0 = nt * BNI, col_end = min(col0 + BNI, p.n_valid);
                 int seg_start, seg_len;
                 xbhead::segment(col0, col_end, p.n_base, p.expand, seg_start, seg_len);
@@ -312,7 +319,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                             if (jj < ncols) sts_f32(sr + 4u * jj, v[jj]);
                     }
                     __syncwarp();
-                    if (dbg) p.dbg[6] += clock64() - te0;
+                    if (dbg) p.dbg[6] += IP_CLK() - te0;
                     // four rows per round, all shared-memory loads before the stores: with only four epilogue warps per SM
                     // a load -> store chain per row segment leaves the copy-out latency-bound
                     float *obase = reinterpret_cast<float *>(p.out) + seg_start + lane;
@@ -339,7 +346,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                             }
                         }
                     }
-                    if (dbg) p.dbg[7] += clock64() - te0;
+                    if (dbg) p.dbg[7] += IP_CLK() - te0;
                 }
             }
             __syncwarp();
@@ -356,7 +363,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                 mbar_wait(&acc_full[(nit - 1) & 1], ((nit - 1) >> 1) & 1);
                 tc_fence_after();
             }
-            const long long tl0 = clock64();
+            const long long tl0 = IP_CLK();
             if (!XCP && valid && set == 0) {   // x block -> tensor memory (lane = row, column c holds elements k = 2c, 2c+1).  The tensor pipe idles
                 // during this, so it has to be quick: a direct row-per-thread read costs one L1 wavefront per lane
                 // (12 k wavefronts per tile, ~20 k cycles).  Instead a warp reads its 32 rows coalesced, 128 bytes
@@ -409,7 +416,7 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                     if (lane == 0) mbar_arrive(&a_ready[kb0 / KPS]);
                 }
             }
-            if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) p.dbg[5] += clock64() - tl0;
+            if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) p.dbg[5] += IP_CLK() - tl0;
             // nt = -1: the previous tile's last N tile (its accumulator was awaited above), then N tiles 0 .. NT-2 of this one
             for (int nt = -1; nt < (valid ? NT - 1 : 0); nt++) {
                 int em0, ent;
@@ -456,15 +463,18 @@ static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaSt
     CUtensorMap tmW, tmX;
     if (int rc = xb_make_tmap_hview(h, &tmW, w, w_rows, BNI, KPS)) return rc;
     if (int rc = xb_make_tmap_hview(h, &tmX, p.x, (uint64_t)p.M, BM, 2)) return rc;
-    static const bool regload = getenv("XB_INPROJ_REGLOAD") != nullptr;     // the earlier x path through registers / staging rows
     p.NT = w_rows / BNI;
     p.dbg = nullptr;
+    p.no_prefetch = 0;
+#ifdef XB_EXPERIMENTS
+    static const bool regload = getenv("XB_INPROJ_REGLOAD") != nullptr;     // the earlier x path through registers / staging rows
     p.no_prefetch = getenv("XB_INPROJ_NOPF") ? 1 : 0;
     if (getenv("XB_INPROJ_DEBUG")) {
         static long long *d = nullptr;
         if (!d) cudaMalloc(&d, 64);
         p.dbg = d;
     }
+#endif
     const int ntiles = (p.M + BM - 1) / BM;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
     constexpr int SMEM_BYTES = IPCfg<EPI>::SMEM_BYTES;
@@ -479,10 +489,14 @@ static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaSt
         return XB_OK;
     };
     int rc;
-    if (h->bf16) rc = regload ? go(inproj_kernel<true, EPI, false>, 0) : go(inproj_kernel<true, EPI, true>, 1);
-    else rc = regload ? go(inproj_kernel<false, EPI, false>, 2) : go(inproj_kernel<false, EPI, true>, 3);
+#ifdef XB_EXPERIMENTS
+    if (regload) rc = go(inproj_kernel<false, EPI, false>, 2);
+    else
+#endif
+    rc = go(inproj_kernel<false, EPI, true>, 3);       // fp16 operands in both weight modes (xb_api.cu repack)
     if (rc) return rc;
     XB_LAUNCH_CHECK(h);
+#ifdef XB_EXPERIMENTS
     if (p.dbg) {
         long long v[8];
         cudaDeviceSynchronize();
@@ -490,6 +504,7 @@ static int ip_launch(xb_handle *h, const void *w, int w_rows, IPParams p, cudaSt
         fprintf(stderr, "inproj MMA thread of CTA 0: %lld tiles; stall cycles: acc_empty %lld, full %lld, a_ready %lld; issue %lld; x-block load (warp 4) %lld; head epilogue stage %lld, stage+copy %lld\n", v[4], v[0], v[1], v[3], v[2], v[5], v[6], v[7]);
         cudaMemset(p.dbg, 0, 64);
     }
+#endif
     return XB_OK;
 }
 

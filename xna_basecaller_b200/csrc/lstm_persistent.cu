@@ -30,10 +30,11 @@
 // Warp roles: warps 0..SUB-1 drive one sub-batch each (one elected thread: counter poll, h boxes, then the step's
 // MMAs part by part as the boxes land, commit; plus the G prefetch), warp SUB allocates tensor memory, epilogue
 // warps start at the next multiple of four, EW (= 8) per sub-batch (warp % 4 = TMEM lane
-// quarter; the second four take the upper half of the chunk columns).  XB_LSTM_VARIANT selects the measured
-// alternatives (1: four epilogue warps, 2: six sub-batches of 16 chunks, 3: two of 48 chunks with twelve epilogue warps,
-// 4: four of 32 chunks with four epilogue warps each and a single G buffer per sub-batch -- 96 CTAs at N = 512),
-// XB_LSTM_WARP_RELEASE=1 the per-warp release.
+// quarter; the second four take the upper half of the chunk columns).  A build with -DXB_EXPERIMENTS adds the measured
+// alternatives behind XB_LSTM_VARIANT (1: four epilogue warps, 2: six sub-batches of 16 chunks, 3: two of 48 chunks with
+// twelve epilogue warps, 4: four of 32 chunks with four epilogue warps each and a single G buffer per sub-batch -- 96 CTAs
+// at N = 512), the per-warp release (XB_LSTM_WARP_RELEASE=1) and the step timeline (XB_LSTM_DEBUG=1); the product
+// library contains the one configuration below and reads no environment variables.
 #include <stdlib.h>
 
 #include "xb_common.cuh"
@@ -86,10 +87,14 @@ struct PLParams {
     int *counters;              // G * SUB counters, CTR_STRIDE ints apart, zeroed before launch
     int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
     int prefetch_y;             // d > 0: prefetch the y rows of step s+d into L2
-    long long *dbg;             // optional timeline (XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
+    long long *dbg;             // optional timeline (XB_EXPERIMENTS, XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
 };
 
+#ifdef XB_EXPERIMENTS
 #define DBG(sub_, ev) do { if (p.dbg && blockIdx.x == 0 && s >= 64 && s < 72) p.dbg[((s - 64) * 8 + (sub_)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define DBG(sub_, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
@@ -230,11 +235,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     const int tp = p.reverse ? t + 1 : t - 1;
                     const int need = TILES * EW * s;         // every epilogue warp of the group has published step s-1
                     DBG(sub, 0);
-                    // relaxed poll (an acquire load costs a CCTL.IVALL per iteration and ~600 cycles per hand-off):
-                    // the producers' release made h visible in L2 before the counter moved, and the only reader of
-                    // that data is the TMA unit, which is issued after (control dependence) and reads L2 directly
+                    // relaxed spin (an acquire load per iteration costs a CCTL.IVALL each time), then ONE acquire load of
+                    // the counter once it has been seen at its target: that load synchronises with the producers'
+                    // red.release (PTX memory model: a relaxed load alone does not), the proxy fence then orders the
+                    // TMA unit's reads of h behind it
                     while (ld_relaxed_gpu(ctr) < need) {
                     }
+                    (void)ld_acquire_gpu(ctr);
                     DBG(sub, 1);
                     fence_proxy_async_global();
                     // h_{t-1} of the sub-batch: HP boxes {64 k, NS chunks, KPB k-blocks}, each landing as KPB
@@ -388,9 +395,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             uint16_t *st = GB == 2 ? reinterpret_cast<uint16_t *>(stage + ((sub * EW + ew) * C::STAGE_BYTES))
                                    : const_cast<uint16_t *>(Gs) + col0 * 128 + q * 32;
             if (GB == 1) __syncwarp();                           // every lane has taken its G values
-#pragma unroll
             // explicit shared-memory instructions: behind the casts the compiler falls back to generic loads / stores
             const uint32_t st_s = smem_u32(st);
+#pragma unroll
             for (int i = 0; i < CELLS; i++) {
                 typename X::T hv = X::from(hout[i]);
                 sts_u16(st_s + 2u * ((8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul), *reinterpret_cast<uint16_t *>(&hv));
@@ -434,6 +441,8 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
     if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
     if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
     const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
+    if (max_groups < 1)
+        return xb_fail(h, XB_ERR_UNSUPPORTED, "the persistent LSTM needs %d co-resident CTAs, the device has %d SMs", TILES, h->num_sms);
     const int block_cap = max_groups * C::NB;
     auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW, GB>;
     static bool configured[64] = {};      // per device: function attributes live in the device's context
@@ -450,9 +459,14 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
         p.w_hh = reinterpret_cast<const uint16_t *>(h->lstm[layer].w_hh);
         p.y = reinterpret_cast<uint16_t *>(y_tnc);
         p.counters = h->lstm_counters;
-        p.one_release = getenv("XB_LSTM_WARP_RELEASE") ? 0 : 1;
-        p.prefetch_y = getenv("XB_LSTM_PREFETCH_Y") ? atoi(getenv("XB_LSTM_PREFETCH_Y")) : 4;
-        p.dbg = getenv("XB_LSTM_DEBUG") ? reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE) : nullptr;
+        p.one_release = 1;
+        p.prefetch_y = 4;
+        p.dbg = nullptr;
+#ifdef XB_EXPERIMENTS
+        if (getenv("XB_LSTM_WARP_RELEASE")) p.one_release = 0;
+        if (getenv("XB_LSTM_PREFETCH_Y")) p.prefetch_y = atoi(getenv("XB_LSTM_PREFETCH_Y"));
+        if (getenv("XB_LSTM_DEBUG")) p.dbg = reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE);
+#endif
         XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, MAX_CTRS * CTR_STRIDE * sizeof(int), s));
         void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
         XB_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, dim3(p.G * TILES), dim3(C::THREADS), args, C::SMEM_BYTES, s));
@@ -463,6 +477,7 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
 
 }  // namespace
 
+#ifdef XB_EXPERIMENTS
 // debug: copy the timeline of the last launch (8 steps x 16 stamps) to the host
 extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
     if (!h || !h->lstm_counters) return XB_ERR_STATE;
@@ -470,6 +485,7 @@ extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
     XB_CUDA(h, cudaMemcpy(out_host, h->lstm_counters + MAX_CTRS * CTR_STRIDE, 8 * 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return XB_OK;
 }
+#endif
 
 // Recurrent part of one LSTM layer.  h->gates must already hold the input projection (T*N, 3072) with the
 // columns of every 128-wide tile ordered [unit][i,f,g,o] (weight repack mode 3 in xb_api.cu).
@@ -479,19 +495,16 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
         XB_CUDA(h, cudaMalloc(&q, MAX_CTRS * CTR_STRIDE * sizeof(int) + 8 * 8 * 16 * sizeof(long long)));
         h->lstm_counters = reinterpret_cast<int *>(q);
     }
+#ifdef XB_EXPERIMENTS
     static const int variant = getenv("XB_LSTM_VARIANT") ? atoi(getenv("XB_LSTM_VARIANT")) : 0;
     if (variant == 1)
-        return h->bf16 ? launch_cfg<true, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s)
-                       : launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
+        return launch_cfg<false, 3, 32, 4>(h, layer, y_tnc, T, N, reverse, s);
     if (variant == 4)      // four chains of 32 chunks on 24 x 4 = 96 CTAs at N = 512 (feasibility of the overlap plan)
-        return h->bf16 ? launch_cfg<true, 4, 32, 4, 1>(h, layer, y_tnc, T, N, reverse, s)
-                       : launch_cfg<false, 4, 32, 4, 1>(h, layer, y_tnc, T, N, reverse, s);
+        return launch_cfg<false, 4, 32, 4, 1>(h, layer, y_tnc, T, N, reverse, s);
     if (variant == 3)
-        return h->bf16 ? launch_cfg<true, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s)
-                       : launch_cfg<false, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s);
+        return launch_cfg<false, 2, 48, 12>(h, layer, y_tnc, T, N, reverse, s);
     if (variant == 2)
-        return h->bf16 ? launch_cfg<true, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s)
-                       : launch_cfg<false, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s);
-    return h->bf16 ? launch_cfg<true, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s)
-                   : launch_cfg<false, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s);
+        return launch_cfg<false, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s);
+#endif
+    return launch_cfg<false, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s);
 }

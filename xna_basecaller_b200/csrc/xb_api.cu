@@ -66,7 +66,6 @@ int dev_alloc_bytes(xb_handle *h, void **p, size_t bytes) { return dev_alloc<uin
 template <bool BF16>
 __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restrict__ dst, int rows_dst, int cols_dst,
                               int rows_src, int cols_src, int mode) {
-    using X = xb16<BF16>;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows_dst * cols_dst) return;
     int r = (int)(i / cols_dst), c = (int)(i % cols_dst);
@@ -86,7 +85,13 @@ __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restric
         int tap = c >> 4, ch = c & 15;
         if (tap < XB_WINLEN) v = src[((size_t)r * XB_C2_CH + ch) * XB_WINLEN + tap];
     }
-    typename X::T hv = X::from(v);
+    // Every kernel multiplies fp16 operands.  XB_FLAG_BF16 ("bf16 weights") rounds the weight to bfloat16 first -- the
+    // value a bf16 checkpoint / bf16 autocast holds -- and stores that number as fp16: 8 mantissa bits fit into 11, so the
+    // conversion is exact for every weight above the fp16 subnormal range (|w| >= 6e-5; below it the absolute error is
+    // <= 3e-8).  tcgen05 kind::f16 does not accept an fp16 x bf16 operand pair (illegal instruction, measured), and
+    // bf16 activations (h, the hoisted input projection) would cost 5x the score error (tests/precision_attribution.py).
+    if (BF16) v = __bfloat162float(__float2bfloat16_rn(v));
+    __half hv = __float2half_rn(v);
     dst[i] = *reinterpret_cast<uint16_t *>(&hv);
 }
 __global__ void lstm_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ dst,
@@ -291,7 +296,12 @@ int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float
     XB_REQUIRE(h, layer >= 0 && layer < 5, "LSTM layer %d out of range", layer);
     XB_REQUIRE(h, w_ih && w_hh && b_ih && b_hh, "NULL LSTM weight");
     const int F = XB_FEATURES;
+#ifdef XB_EXPERIMENTS
+#define XB_FLAG_LSTM_STEPWISE 4
     const int ih_mode = (h->flags & XB_FLAG_LSTM_STEPWISE) ? 1 : 3;
+#else
+    const int ih_mode = 3;
+#endif
     if (int rc = repack(h, w_ih, h->lstm[layer].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
     if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, ih_mode == 3 ? 4 : 1, s)) return rc;
     lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(b_ih, b_hh, h->lstm[layer].bias, ih_mode);
@@ -362,37 +372,42 @@ int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, 
     // (a) input projection for all time steps: gates (T*N, 3072) = x W_ih^T + (b_ih + b_hh)
     {
         xb_stage_timer tm(h, XB_ST_INPROJ, s);
+#ifdef XB_EXPERIMENTS
         static const bool generic = getenv("XB_INPROJ_GENERIC") != nullptr;    // A/B switch: the generic tile kernel
-        if (!generic) {
-            if (int rc = xb_inproj_launch(h, x_tnc, lw.w_ih, lw.bias, h->gates, T * N, s)) return rc;
-        } else {
-        CUtensorMap tmA, tmB;
-        if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
-        if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_ih, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
-        GemmParams p;
-        p.M = T * N; p.N = XB_GATES; p.K = XB_FEATURES;
-        p.bias = lw.bias; p.out = h->gates; p.ldo = XB_GATES;
-        if (int rc = xb_gemm_launch(h, EPI_INPROJ, tmA, tmB, p, s)) return rc;
-        }
+        if (generic) {
+            CUtensorMap tmA, tmB;
+            if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+            if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_ih, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
+            GemmParams p;
+            p.M = T * N; p.N = XB_GATES; p.K = XB_FEATURES;
+            p.bias = lw.bias; p.out = h->gates; p.ldo = XB_GATES;
+            if (int rc = xb_gemm_launch(h, EPI_INPROJ, tmA, tmB, p, s)) return rc;
+        } else
+#endif
+        if (int rc = xb_inproj_launch(h, x_tnc, lw.w_ih, lw.bias, h->gates, T * N, s)) return rc;
     }
-    // (b) recurrence: one fused GEMM + cell kernel per time step; direction by indexing
+    // (b) recurrence: one persistent launch per layer; direction by indexing
     xb_stage_timer tm(h, XB_ST_LSTM_REC, s);
-    if (!(h->flags & XB_FLAG_LSTM_STEPWISE)) return xb_lstm_recurrence_persistent(h, layer, y_tnc, T, N, reverse, s);
-    CUtensorMap tmH, tmW;
-    if (int rc = xb_make_tmap_2d(h, &tmH, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
-    if (int rc = xb_make_tmap_2d(h, &tmW, lw.w_hh, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
-    for (int i = 0; i < T; i++) {
-        const int t = reverse ? T - 1 - i : i;
-        const int tp = reverse ? t + 1 : t - 1;
-        GemmParams p;
-        p.M = N; p.N = XB_GATES; p.K = XB_FEATURES;
-        p.a_row_offset = (i == 0) ? 0 : tp * N;
-        p.out = y_tnc; p.NB = N;
-        p.gates = h->gates; p.cstate = h->cstate;
-        p.t_cur = t; p.first = (i == 0);
-        if (int rc = xb_gemm_launch(h, EPI_LSTM, tmH, tmW, p, s)) return rc;
+#ifdef XB_EXPERIMENTS
+    if (h->flags & XB_FLAG_LSTM_STEPWISE) {      // one fused GEMM + cell kernel per time step (independent cross-check)
+        CUtensorMap tmH, tmW;
+        if (int rc = xb_make_tmap_2d(h, &tmH, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+        if (int rc = xb_make_tmap_2d(h, &tmW, lw.w_hh, XB_GATES, XB_FEATURES, XB_FEATURES)) return rc;
+        for (int i = 0; i < T; i++) {
+            const int t = reverse ? T - 1 - i : i;
+            const int tp = reverse ? t + 1 : t - 1;
+            GemmParams p;
+            p.M = N; p.N = XB_GATES; p.K = XB_FEATURES;
+            p.a_row_offset = (i == 0) ? 0 : tp * N;
+            p.out = y_tnc; p.NB = N;
+            p.gates = h->gates; p.cstate = h->cstate;
+            p.t_cur = t; p.first = (i == 0);
+            if (int rc = xb_gemm_launch(h, EPI_LSTM, tmH, tmW, p, s)) return rc;
+        }
+        return XB_OK;
     }
-    return XB_OK;
+#endif
+    return xb_lstm_recurrence_persistent(h, layer, y_tnc, T, N, reverse, s);
 }
 
 int xb_lstm_stack_fwd(xb_handle *h, void *x_tnc, void *y_tnc, int T, int N, void *stream) {
@@ -414,20 +429,23 @@ int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     xb_stage_timer tm(h, XB_ST_HEAD, s);
+#ifdef XB_EXPERIMENTS
     static const bool tile_gemm = getenv("XB_HEAD_GENERIC") != nullptr;      // the 128x128 tile GEMM, kept for cross-checks
-    if (!tile_gemm)
-        return xb_head_astationary_launch(h, x_tnc, h->head_w, h->head_rows_padded, h->head_b, h->head_rows, scores,
-                                          h->expand_blanks ? h->C * h->NZ : h->head_rows, T * N, s);
-    CUtensorMap tmA, tmB;
-    if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
-    if (int rc = xb_make_tmap_2d(h, &tmB, h->head_w, h->head_rows_padded, XB_FEATURES, XB_FEATURES)) return rc;
-    GemmParams p;
-    p.M = T * N; p.N = h->head_rows_padded; p.K = XB_FEATURES;
-    p.bias = h->head_b; p.out = scores;
-    p.ldo = h->expand_blanks ? h->C * h->NZ : h->head_rows;
-    p.n_base = h->n_base; p.head_rows = h->head_rows; p.expand = h->expand_blanks;
-    p.scale = h->scale; p.blank = h->blank_score;
-    return xb_gemm_launch(h, EPI_HEAD, tmA, tmB, p, s);
+    if (tile_gemm) {
+        CUtensorMap tmA, tmB;
+        if (int rc = xb_make_tmap_2d(h, &tmA, x_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES)) return rc;
+        if (int rc = xb_make_tmap_2d(h, &tmB, h->head_w, h->head_rows_padded, XB_FEATURES, XB_FEATURES)) return rc;
+        GemmParams p;
+        p.M = T * N; p.N = h->head_rows_padded; p.K = XB_FEATURES;
+        p.bias = h->head_b; p.out = scores;
+        p.ldo = h->expand_blanks ? h->C * h->NZ : h->head_rows;
+        p.n_base = h->n_base; p.head_rows = h->head_rows; p.expand = h->expand_blanks;
+        p.scale = h->scale; p.blank = h->blank_score;
+        return xb_gemm_launch(h, EPI_HEAD, tmA, tmB, p, s);
+    }
+#endif
+    return xb_head_astationary_launch(h, x_tnc, h->head_w, h->head_rows_padded, h->head_b, h->head_rows, scores,
+                                      h->expand_blanks ? h->C * h->NZ : h->head_rows, T * N, s);
 }
 
 int xb_encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, void *stream) {

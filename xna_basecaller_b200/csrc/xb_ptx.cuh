@@ -216,7 +216,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// cute::UMMA::InstrDescriptor for kind::f16: D fp32, A/B both fp16 (fmt 0) or bf16 (fmt 1), K-major, M x N
+// cute::UMMA::InstrDescriptor for kind::f16: D fp32, A/B both fp16 (fmt 0) or both bf16 (fmt 1), K-major, M x N.
+// (The descriptor has one format field per operand, but an fp16 x bf16 pair raises an illegal-instruction error on
+// B200 -- measured in round 2 -- so "bf16 weights" are stored as the fp16 numbers they are, see repack_kernel.)
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

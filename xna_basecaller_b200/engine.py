@@ -37,8 +37,9 @@ class Engine:
             max_N = max(N, h.max_N if h is not None and h.device == device else 0)
             max_T = max(T, h.max_T if h is not None and h.device == device else 0)
             need_enc = encoder or (h is not None and h.has_encoder)
-            if h is not None:
-                h.close()
+            # The outgoing handle is NOT destroyed here: an in-flight pipelined batch (crf/basecall.py::_submit_scores), a
+            # _CTCLoss context between forward and backward or a ReadSetBasecaller may still hold it.  Dropping our
+            # reference lets Handle.__del__ run xb_destroy when its last user lets go.
             self.handle = _lib.Handle(self.alphabet, self.state_len, max_N=max_N, max_T=max_T, device=device,
                                       bf16=bf16, encoder=need_enc)
             self.handle.has_encoder = need_enc

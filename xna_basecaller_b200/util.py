@@ -186,10 +186,12 @@ def match_names(state_dict, model, skip_layers=()):
 
 
 def load_model(dirname, device, weights=None, half=None, chunksize=None, batchsize=None, overlap=None,
-               quantize=False, use_koi=False, skip_top=False):
+               quantize=False, use_koi=False, skip_top=False, drop_rate=None, drop_rate_bottom=None):
     """Build Model from <dirname>/config.toml and load weights_<n>.tar (latest when weights is None):
-    the same directory layout, overrides and key remapping as the reference loader.  `quantize` / `use_koi`
-    are accepted and ignored (koi is bypassed for UB alphabets, bonito/util.py:299-301)."""
+    the same directory layout, overrides and key remapping as the reference loader (bonito/util.py:261-366).
+    Flags override the config with the reference's `value or config` rule for chunksize / batchsize (0 falls back
+    to the config) and `is not None` for overlap / drop rates.  `quantize` / `use_koi` are accepted and ignored (koi
+    is bypassed for UB alphabets, bonito/util.py:299-301)."""
     if not os.path.isdir(dirname) and os.path.isdir(os.path.join(__models__, dirname)):
         dirname = os.path.join(__models__, dirname)
     if not weights:
@@ -199,18 +201,23 @@ def load_model(dirname, device, weights=None, half=None, chunksize=None, batchsi
         weights = max(int(re.sub(r'.*_([0-9]+)\.tar', r'\1', w)) for w in found)
     config = _load_toml(os.path.join(dirname, 'config.toml'))
     bc = config.setdefault('basecaller', {})
-    for name, val in (('chunksize', chunksize), ('overlap', overlap), ('batchsize', batchsize)):
-        if val is not None:
-            bc[name] = val
-        bc.setdefault(name, {'chunksize': 4000, 'overlap': 500, 'batchsize': 64}[name])
+    bc['chunksize'] = chunksize or bc.get('chunksize', 4000)
+    bc['overlap'] = overlap if overlap is not None else bc.get('overlap', 500)
+    bc['batchsize'] = batchsize or bc.get('batchsize', 64)
+    enc = config.setdefault('encoder', {})
+    enc['drop_rate'] = drop_rate if drop_rate is not None else enc.get('drop_rate', 0)
+    enc['drop_rate_bottom'] = drop_rate_bottom if drop_rate_bottom is not None else enc.get('drop_rate_bottom', 0)
     Model = load_symbol(config, 'Model')
     model = Model(config)
     path = os.path.join(dirname, 'weights_%s.tar' % weights)
     state = torch.load(path, map_location='cpu')
     state = {k.replace('module.', ''): v for k, v in state.items()}
-    skip = [k for k in state if skip_top and k.startswith('encoder.9.')]
+    skip = [k for k in model.state_dict() if k.startswith('encoder.9')] if skip_top else []
     names = match_names(state, model, skip)
-    model.load_state_dict(OrderedDict((names[k], v) for k, v in state.items() if k in names), strict=not skip_top)
+    result = model.load_state_dict(OrderedDict((names[k], v) for k, v in state.items() if k in names),
+                                   strict=not skip_top)
+    assert list(result.unexpected_keys) == [], 'checkpoint holds tensors the model does not: %s' % result.unexpected_keys
+    assert list(result.missing_keys) == skip, 'model tensors missing from the checkpoint: %s' % result.missing_keys
     if half is None:
         half = half_supported()
     if half:
