@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XB_ABI_VERSION 1
+#define XB_ABI_VERSION 2
 
 typedef struct xb_handle xb_handle;
 
@@ -125,6 +125,22 @@ int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labe
 int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring,
                   int32_t *lens, int8_t *labels_nt, float *post, void *stream);
 
+/* The fused route's hand-over format.  decode_batch is computed in the linear domain (sums / maxima of products of
+ * E = exp(score), see csrc/crf_decode_lin.cu); when encoder and decode run back to back the CRF head writes E itself
+ * -- one bit-reproducible exponential per edge instead of one in each of the three decode sweeps -- and the decode
+ * reads it.  xb_crf_head_fwd_exp is xb_crf_head_fwd with that exponential applied (blank included),
+ * xb_crf_decode_exp is xb_crf_decode on such a tensor; xb_crf_decode_exp(xb_crf_head_fwd_exp(x)) returns the bits of
+ * xb_crf_decode(xb_crf_head_fwd(x)).  Scores outside [-80, 80] are clamped before the exponential on both routes. */
+int xb_crf_head_fwd_exp(xb_handle *h, const void *x_tnc, float *escores, int T, int N, void *stream);
+int xb_crf_decode_exp(xb_handle *h, const float *escores, int T, int N, int8_t *seq, int8_t *qstring,
+                      int32_t *lens, int8_t *labels_nt, float *post, void *stream);
+
+/* compute_scores between its two copies (crf/basecall.py:47-76) for chunks already on the device: encoder + decode over
+ * signal (N, L) of sig_dtype -> seq / qstring (N, T) int8 left-packed, lens (N); qstring may be NULL.  The scores
+ * stay in handle workspace (in the hand-over format above). */
+int xb_basecall_chunks(xb_handle *h, const void *signal, int sig_dtype, int N, int L, int8_t *seq, int8_t *qstring,
+                       int32_t *lens, void *stream);
+
 /* CTC_CRF.ctc_loss(reduction='none') forward (crf/model.py:118-131): targets (N, Lmax) int32 1-based
  * 0-padded, lengths (N) int32 -> loss (N) fp32 = -logz / length.  normalise as in the reference. */
 int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets,
@@ -143,10 +159,11 @@ int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const i
 /* util.stitch over left-packed chunks (util.py:169-188; crf/basecall.py:15-24): for each read r,
  * concatenates slices of its chunks' packed rows.  chunk_first[r], chunk_count[r], read_len[r]
  * (samples) describe the reads; rows are (n_chunks_total, T) int8; out is (n_reads, out_stride) int8,
- * out_len (n_reads). */
+ * out_len (n_reads).  reverse != 0 is the reference's reverse=True branch (util.py:180-184; `bonito basecaller
+ * --reverse`): chunks walked backwards, slices taken from the end of each row with Python's negative-index rules. */
 int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first,
               const int32_t *chunk_count, const int32_t *read_len, int n_reads, int chunksize,
-              int overlap, int stride, int8_t *out, int out_stride, int32_t *out_len, void *stream);
+              int overlap, int stride, int reverse, int8_t *out, int out_stride, int32_t *out_len, void *stream);
 
 /* util.chunk (util.py:152-166) for a whole read set resident on the device: signal holds the reads back to back
  * (sig_dtype XB_SIG_F32 or XB_SIG_I16), read r occupies [read_offset[r], read_offset[r] + read_len[r]); chunk c is

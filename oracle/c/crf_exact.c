@@ -256,21 +256,14 @@ int xbo_crf_decode(const float *scores, int T, int N, int n_base, int state_len,
  *   Max-alpha: v_k = P_t[c,k] * am_hat_t[src(c,k)];  um_{t+1}[c] = max_k v_k,  am_hat_0 = 1
  *   label_t  = (arg-max over the flat edge index c*NZ+k of v_k * bm_hat_{t+1}[c], first index on ties) % NZ
  * lin_input != 0: `scores` already holds E (what the fused head writes). */
-static inline float pow2_scale(float mx) {
-    uint32_t e = (XB_F2U(mx) >> 23) & 0xffu;
-    if (e == 0u || e == 255u || (XB_F2U(mx) >> 31)) return 1.0f;
-    return XB_U2F((254u - e) << 23);
-}
+#define pow2_scale xb_pow2_scale
 static inline float vec_max(const float *v, int C) {
     float m = v[0];
     for (int c = 1; c < C; c++) m = v[c] > m ? v[c] : m;
     return m;
 }
 static inline float edge_E(const float *row, size_t i, int lin_input) {
-    if (lin_input) return row[i];
-    float m = row[i];
-    m = m < -80.0f ? -80.0f : (m > 80.0f ? 80.0f : m);
-    return xb_expf(m);
+    return lin_input ? row[i] : xb_score_exp(row[i]);
 }
 
 int xbo_crf_decode_lin_range(const float *scores, int lin_input, int T, int N, int n_begin, int n_end, int n_base,
@@ -416,6 +409,7 @@ int xbo_pack(const int8_t *labels, int N, int T, const char *alphabet, int8_t *s
     return 0;
 }
 
+void xbo_score_exp_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_score_exp(x[i]); }
 void xbo_expf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_expf(x[i]); }
 void xbo_logf_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_logf(x[i]); }
 void xbo_expf_le0_array(const float *x, float *y, long n) { for (long i = 0; i < n; i++) y[i] = xb_expf_le0(x[i]); }

@@ -68,6 +68,11 @@ def expf_le0(x):
     return _apply('xbo_expf_le0_array', x)
 
 
+def score_exp(x):
+    """exp of a CRF score as the linear-domain decode defines it (clamp to [-80, 80], xb_expf_mid)."""
+    return _apply('xbo_score_exp_array', x)
+
+
 def logf_norm(x):
     return _apply('xbo_logf_norm_array', x)
 
@@ -89,8 +94,9 @@ def crf_logz(scores, n_base, state_len=3):
     return out
 
 
-def crf_decode(scores, n_base, state_len=3, want_post=False, want_lp=False):
-    """labels (N,T) int8 [, posteriors (T,N,C*NZ)] [, log(post+1e-8) (T,N,C*NZ)]."""
+def crf_decode_logdomain(scores, n_base, state_len=3, want_post=False, want_lp=False):
+    """The log-domain restatement of decode_batch (round 1's kernel contract), kept as an independent second
+    formulation to cross-check the linear-domain one: labels (N,T) int8 [, posteriors] [, log(post+1e-8)]."""
     s = _f32(scores)
     T, N, _ = s.shape
     labels = np.empty((N, T), dtype=np.int8)
@@ -107,27 +113,11 @@ def crf_decode(scores, n_base, state_len=3, want_post=False, want_lp=False):
     return out[0] if len(out) == 1 else tuple(out)
 
 
-def crf_decode_threads(scores, n_base, state_len=3, threads=1):
-    """crf_decode with the batch spread over `threads` host threads (ctypes releases the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
-    s = _f32(scores)
-    T, N, _ = s.shape
-    labels = np.empty((N, T), dtype=np.int8)
-    threads = max(1, min(threads, N))
-    bounds = [(N * i // threads, N * (i + 1) // threads) for i in range(threads)]
-    fn = lib().xbo_crf_decode_range
-
-    def work(b):
-        return fn(_p(s), T, N, b[0], b[1], n_base, state_len, None, None, _p(labels))
-
-    with ThreadPoolExecutor(threads) as ex:
-        assert all(rc == 0 for rc in ex.map(work, bounds))
-    return labels
-
-
-def crf_decode_lin(scores, n_base, state_len=3, want_post=False, lin_input=False, threads=1):
-    """Linear-domain (scaled) decode, the contract of the CUDA decode kernels: labels (N,T) int8 [, posteriors].
-    lin_input: `scores` already holds exp(scores) (what the fused head hands to the decode)."""
+def crf_decode(scores, n_base, state_len=3, want_post=False, exp_input=False, threads=1):
+    """decode_batch as the CUDA kernels compute it -- the linear-domain (scaled) contract written above
+    xbo_crf_decode_lin_range in c/crf_exact.c: labels (N,T) int8 [, posteriors (T,N,C*NZ)].
+    exp_input: `scores` already holds exp(scores) (what the fused head hands to the decode).
+    threads > 1 spreads the batch over host threads (ctypes releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     s = _f32(scores)
     T, N, _ = s.shape
@@ -138,11 +128,15 @@ def crf_decode_lin(scores, n_base, state_len=3, want_post=False, lin_input=False
     fn = lib().xbo_crf_decode_lin_range
 
     def work(b):
-        return fn(_p(s), int(lin_input), T, N, b[0], b[1], n_base, state_len, _p(post) if want_post else None, _p(labels))
+        return fn(_p(s), int(exp_input), T, N, b[0], b[1], n_base, state_len, _p(post) if want_post else None, _p(labels))
 
     with ThreadPoolExecutor(threads) as ex:
         assert all(rc == 0 for rc in ex.map(work, bounds))
     return (labels, post) if want_post else labels
+
+
+def crf_decode_threads(scores, n_base, state_len=3, threads=1):
+    return crf_decode(scores, n_base, state_len, threads=threads)
 
 
 def crf_viterbi(scores, n_base, state_len=3):

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_path(lib):
-    assert lib.xb_abi_version() == 1
+    assert lib.xb_abi_version() == 2
     if torch.cuda.is_available():
         pytest.skip('error path without a device is only observable on a CPU-only host')
     h = ctypes.c_void_p()

@@ -23,6 +23,10 @@ def _worker(rank, world, port, out):
     counters = {'reads': len(mine), 'samples': int(lengths[mine].sum()), 'chunks': len(plan['chunk_read']),
                 'seconds': 1.0 + rank}
     table = pipeline.gather_counters(counters)
+    # dynamic work queue over the group's store: the two ranks together take every block exactly once
+    store = dist.distributed_c10d._get_default_store()
+    took = list(pipeline.WorkQueue(37, store=store, key='wq_test'))
+    table['took'] = pipeline.gather_counters({'n': len(took), 'sum': sum(took), 'sumsq': sum(k * k for k in took)})
     if rank == 0:
         torch.save(table, out)
     dist.barrier()
@@ -39,8 +43,11 @@ def test_two_rank_sharding_and_counter_gather(tmp_path):
     assert sum(table['samples']) == float(lengths.sum())
     assert table['seconds'] == [1.0, 2.0]
     assert sum(table['chunks']) > 101
+    took = table['took']
+    assert sum(took['n']) == 37 and sum(took['sum']) == sum(range(37)) and sum(took['sumsq']) == sum(k * k for k in range(37))
 
 
 def test_single_process_counter_gather():
     from xna_basecaller_b200 import pipeline
     assert pipeline.gather_counters({'a': 3, 'b': 0.5}) == {'a': [3.0], 'b': [0.5]}
+    assert list(pipeline.WorkQueue(5)) == [0, 1, 2, 3, 4]

@@ -157,6 +157,23 @@ def test_encoder_bf16_option():
     h.close()
 
 
+def test_head_exp_mode_and_fused_route(enc5):
+    """The CRF head's exp epilogue writes exactly xb_score_exp(score) (blank column included), and the fused
+    xb_basecall_chunks route (head -> exp(scores) -> linear-domain decode) returns the packed rows of the two-call route."""
+    from oracle import cexact
+    h, sd = enc5
+    g = torch.Generator().manual_seed(8)
+    x = (torch.rand(70, 5, 768, generator=g) * 2 - 1).half().cuda()
+    s = h.crf_head(x)
+    e = h.crf_head(x, exp=True)
+    assert np.array_equal(e.cpu().numpy().view(np.uint32), cexact.score_exp(s.cpu().numpy()).view(np.uint32))
+    sig = synthetic_signal(27, 6, 1500)
+    seq, _, lens = h.basecall_chunks(sig.cuda())
+    seq2, _, lens2 = h.decode(h.encoder(sig.cuda()), want_qstring=False)
+    assert torch.equal(seq, seq2) and torch.equal(lens, lens2)
+    assert int(lens.sum()) > 0
+
+
 def test_compute_scores_host_end_to_end(enc5, golden):
     """H2D -> encoder -> decode -> D2H through the host-buffer entry point, against the reference's
     compute_scores output (left-packed int8 rows)."""

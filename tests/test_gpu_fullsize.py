@@ -35,13 +35,17 @@ def _mixed_decode_handle(x):
     string, a strongly amplified one emits a base at every step; both make decode parity vacuous)."""
     from xna_basecaller_b200._lib import Handle
     h = Handle(ALPHABETS[5], 3, max_N=N_FULL, max_T=L_FULL // 5)
-    for gain in (1.5, 1.25, 2.0, 1.0, 2.5, 3.0):
+    lo, hi, seen = 0.02, 8.0, []                     # decoded length grows with the gain: bisect in log space
+    for _ in range(14):
+        gain = (lo * hi) ** 0.5
         h.load_weights(_weights(gain))
         _, _, lens = h.decode(h.encoder(x[:16]), want_qstring=False)
         mean = lens.float().mean().item()
+        seen.append((round(gain, 3), mean))
         if 100 < mean < 700:
             return h, gain, mean
-    raise AssertionError('no head gain gives a mixed decode')
+        lo, hi = (gain, hi) if mean <= 100 else (lo, gain)
+    raise AssertionError('no head gain gives a mixed decode: %s' % seen)
 
 
 @pytest.fixture(scope='module')

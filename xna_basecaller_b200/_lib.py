@@ -23,7 +23,7 @@ SYMBOLS = (
     'xb_lstm_fwd', 'xb_lstm_stack_fwd', 'xb_crf_head_fwd', 'xb_encoder_fwd', 'xb_crf_logz',
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
     'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_compute_scores_submit', 'xb_compute_scores_wait', 'xb_launch_count', 'xb_gemm_selftest',
-    'xb_set_profiling', 'xb_stage_times',
+    'xb_set_profiling', 'xb_stage_times', 'xb_crf_head_fwd_exp', 'xb_crf_decode_exp', 'xb_basecall_chunks',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
           'crf_backward', 'crf_viterbi')
@@ -62,12 +62,15 @@ def load():
     lib.xb_crf_posteriors.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.xb_crf_decode_exp.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
+    lib.xb_crf_head_fwd_exp.argtypes = [vp, vp, vp, ci, ci, vp]
+    lib.xb_basecall_chunks.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_fwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp]
     lib.xb_compute_scores_submit.argtypes = [vp, ci, vp, ci, ci, vp, vp, vp]
     lib.xb_compute_scores_wait.argtypes = [vp, ci]
     lib.xb_preprocess_reads.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp]
     lib.xb_ctc_crf_loss_bwd.argtypes = [vp, vp, ci, ci, vp, ci, vp, ci, vp, vp, vp, vp]
-    lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp]
+    lib.xb_stitch.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, ci, vp, vp]
     lib.xb_gather_chunks.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp]
     lib.xb_compute_scores_host.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.xb_launch_count.restype = ctypes.c_int64
@@ -218,13 +221,28 @@ class Handle:
         self._check(self.lib.xb_lstm_stack_fwd(self.h, _ptr(x), _ptr(y), T, N, _stream(self.device)), 'xb_lstm_stack_fwd')
         return y
 
-    def crf_head(self, x, expand_blanks=True):
+    def crf_head(self, x, expand_blanks=True, exp=False):
+        """LinearCRFEncoder scores; exp=True: exp(scores), the hand-over format of the fused route."""
         x = x.contiguous()
         T, N, _ = x.shape
         width = self.C * self.NZ if expand_blanks else self.C * self.n_base
         scores = torch.empty(T, N, width, dtype=torch.float32, device=self.device)
-        self._check(self.lib.xb_crf_head_fwd(self.h, _ptr(x), _ptr(scores), T, N, _stream(self.device)), 'xb_crf_head_fwd')
+        fn = self.lib.xb_crf_head_fwd_exp if exp else self.lib.xb_crf_head_fwd
+        self._check(fn(self.h, _ptr(x), _ptr(scores), T, N, _stream(self.device)), 'xb_crf_head_fwd')
         return scores
+
+    def basecall_chunks(self, signal, want_qstring=False, out=None):
+        """Fused encoder + decode of device-resident chunks: (seq (N,T) int8 left-packed, qstring | None, lens (N) int32).
+        out: optional contiguous (N, T) int8 device tensor that receives the packed rows."""
+        signal, code = self._sig(signal.to(self.device))
+        N, L = signal.shape
+        T = L // 5
+        seq = out if out is not None else torch.empty(N, T, dtype=torch.int8, device=self.device)
+        qs = torch.empty(N, T, dtype=torch.int8, device=self.device) if want_qstring else None
+        lens = torch.empty(N, dtype=torch.int32, device=self.device)
+        self._check(self.lib.xb_basecall_chunks(self.h, _ptr(signal), code, N, L, _ptr(seq), _ptr(qs), _ptr(lens),
+                                                _stream(self.device)), 'xb_basecall_chunks')
+        return seq, qs, lens
 
     def encoder(self, signal, expand_blanks=True):
         signal, code = self._sig(signal.to(self.device))
@@ -276,16 +294,18 @@ class Handle:
         self._check(self.lib.xb_crf_viterbi(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)), 'xb_crf_viterbi')
         return out
 
-    def decode(self, scores, want_labels=False, want_post=False, want_qstring=True):
-        """sequence (N,T) int8, qstring (N,T) int8 | None, lens (N) int32 [, labels (N,T)] [, post]."""
+    def decode(self, scores, want_labels=False, want_post=False, want_qstring=True, exp_input=False):
+        """sequence (N,T) int8, qstring (N,T) int8 | None, lens (N) int32 [, labels (N,T)] [, post].
+        exp_input: `scores` holds exp(scores) (crf_head(..., exp=True))."""
         s, T, N = self._scores(scores)
         seq = torch.empty(N, T, dtype=torch.int8, device=self.device)
         qs = torch.empty(N, T, dtype=torch.int8, device=self.device) if want_qstring else None
         lens = torch.empty(N, dtype=torch.int32, device=self.device)
         labels = torch.empty(N, T, dtype=torch.int8, device=self.device) if want_labels else None
         post = torch.empty_like(s) if want_post else None
-        self._check(self.lib.xb_crf_decode(self.h, _ptr(s), T, N, _ptr(seq), _ptr(qs), _ptr(lens), _ptr(labels),
-                                           _ptr(post), _stream(self.device)), 'xb_crf_decode')
+        fn = self.lib.xb_crf_decode_exp if exp_input else self.lib.xb_crf_decode
+        self._check(fn(self.h, _ptr(s), T, N, _ptr(seq), _ptr(qs), _ptr(lens), _ptr(labels),
+                       _ptr(post), _stream(self.device)), 'xb_crf_decode')
         out = [seq, qs, lens]
         if want_labels:
             out.append(labels)
@@ -316,7 +336,7 @@ class Handle:
                     'xb_ctc_crf_loss_bwd')
         return grad
 
-    def stitch(self, rows, chunk_first, chunk_count, read_len, chunksize, overlap, stride=5, out_stride=None):
+    def stitch(self, rows, chunk_first, chunk_count, read_len, chunksize, overlap, stride=5, out_stride=None, reverse=False):
         rows = rows.to(self.device, torch.int8).contiguous()
         T = rows.shape[1]
         cf = torch.as_tensor(chunk_first, dtype=torch.int32, device=self.device)
@@ -328,7 +348,8 @@ class Handle:
         out = torch.zeros(n_reads, out_stride, dtype=torch.int8, device=self.device)
         out_len = torch.empty(n_reads, dtype=torch.int32, device=self.device)
         self._check(self.lib.xb_stitch(self.h, _ptr(rows), T, _ptr(cf), _ptr(cc), _ptr(rl), n_reads, chunksize, overlap,
-                                       stride, _ptr(out), out_stride, _ptr(out_len), _stream(self.device)), 'xb_stitch')
+                                       stride, int(bool(reverse)), _ptr(out), out_stride, _ptr(out_len),
+                                       _stream(self.device)), 'xb_stitch')
         return out, out_len
 
     def gather_chunks(self, signal, read_offset, read_len, chunk_read, chunk_start, L, out=None):

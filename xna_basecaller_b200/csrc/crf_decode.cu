@@ -1,5 +1,6 @@
-// CTC-CRF scans for sm_100a: Log-semiring forward (alpha / logZ), fused backward sweep (beta, posteriors,
-// log-posteriors, Max-semiring beta) and Max-semiring forward sweep with arg-max, labels and left-packing.
+// CTC-CRF scans on RAW scores for sm_100a, in the log domain: Log-semiring forward (alpha / logZ), backward scans in
+// either semiring, Max-semiring forward sweep with arg-max, labels and left-packing (CTC_CRF.logZ / forward_scores /
+// backward_scores / viterbi).  decode_batch (posteriors + max-marginal Viterbi) lives in crf_decode_lin.cu.
 //
 // Reference semantics: bonito/crf/model.py:26-46 (idx, logZ), :51-61 (forward/backward scores), :92-100
 // (viterbi, path_to_str), :215-218 (decode_batch); bonito/crf/basecall.py:56-76 (left-packed rows); the
@@ -151,146 +152,6 @@ crf_bscan_kernel(const float *__restrict__ scores, int T, int N, float *__restri
 }
 
 // --------------------------------------------------------------------------------------------------
-// Fused backward sweep of decode_batch: per step t (descending)
-//   x = (M + alpha_t[idx]) + beta_{t+1};  p = softmax_{C*NZ}(x);  lp = log(p + 1e-8)
-//   beta_t (Log) from M and beta_{t+1};   bmax_t (Max semiring over lp) from lp and bmax_{t+1}
-// writes lp (T,N,S) and bmax (T+1,N,C) for the Max forward sweep, optionally post (T,N,S).
-template <int NB, int SL>
-__global__ void __launch_bounds__(Lat<NB, SL>::NT)
-crf_backward_kernel(const float *__restrict__ scores, const float *__restrict__ alpha, int T, int N,
-                    float *__restrict__ lp_out, float *__restrict__ bmax_out, float *__restrict__ post_out) {
-    using L = Lat<NB, SL>;
-    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
-    extern __shared__ __align__(16) float smem[];
-    float *ringM = smem;                 // D * S
-    float *LP = ringM + D * S;           // S
-    float *ringA = LP + S;               // D * NT
-    float *beta = ringA + D * NT;        // 2 * NT
-    float *bm = beta + 2 * NT;           // 2 * NT
-    float *red = bm + 2 * NT;            // 2 * W
-    float *FS = red + 2 * W;             // NT
-    const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
-    const bool act = c < C;
-    const float *base = scores + (size_t)n * S;
-    const size_t row = (size_t)N * S;
-    const float *abase = alpha + (size_t)n * C;
-    const size_t arow = (size_t)N * C;
-
-#pragma unroll
-    for (int j = 0; j < D - 1; j++) {
-        if (j < T) {
-            copy_row<S, NT>(ringM + j * S, base + (size_t)(T - 1 - j) * row);
-            if (act) cp_async4(ringA + j * NT + c, abase + (size_t)(T - 1 - j) * arow + c);
-        }
-        cp_async_commit();
-    }
-    beta[c] = 0.0f;
-    bm[c] = 0.0f;
-    if (act) bmax_out[((size_t)T * N + n) * C + c] = 0.0f;
-    int src[NZ];
-    src[0] = act ? c : 0;
-#pragma unroll
-    for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
-    const int kk = act ? 1 + c / L::NP : 1, cb = act ? (c % L::NP) * NB : 0;
-
-    // running pointers (rows are visited in descending t) instead of per-step 64-bit index arithmetic
-    const float *fetchM = base + (size_t)(T - D) * row;          // row T-1-r for r = D-1
-    const float *fetchA = abase + (size_t)(T - D) * arow + c;
-    for (int i = 0; i < T; i++) {
-        const int t = T - 1 - i;
-        cp_async_wait<D - 2>();
-        __syncthreads();                                                        // B0
-        {
-            int r = i + D - 1;
-            if (r < T) {
-                copy_row<S, NT>(ringM + (r % D) * S, fetchM);
-                if (act) cp_async4(ringA + (r % D) * NT + c, fetchA);
-            }
-            fetchM -= row;
-            fetchA -= arow;
-            cp_async_commit();
-        }
-        const float *M = ringM + (i % D) * S;
-        const float *A = ringA + (i % D) * NT;
-        const float *b1 = beta + (i & 1) * NT;
-        float *b0 = beta + ((i + 1) & 1) * NT;
-        const float *m1 = bm + (i & 1) * NT;
-        float *m0 = bm + ((i + 1) & 1) * NT;
-
-        // Thread c as SOURCE state: z over the edges leaving c (stay, then the n_base moves), w = exp(z - m_c) feeds
-        // both Log beta_t[c] and the softmax numerator exp(x - gmax) = w * f_c, f_c = exp((m_c + alpha_t[c]) - gmax).
-        float g = -INFINITY;
-        if (act) {
-            float z[NZ], m;
-            z[0] = XB_ADD(M[c * NZ], b1[c]);
-            m = z[0];
-#pragma unroll
-            for (int j = 0; j < NB; j++) {
-                z[1 + j] = XB_ADD(M[(cb + j) * NZ + kk], b1[cb + j]);
-                m = fmaxf(m, z[1 + j]);
-            }
-            float sy = 0.0f;
-#pragma unroll
-            for (int j = 0; j < NZ; j++) {
-                float e = xb_expf_le0(XB_SUB(z[j], m));
-                LP[j == 0 ? c * NZ : (cb + j - 1) * NZ + kk] = e;
-                sy = (j == 0) ? e : XB_ADD(sy, e);
-            }
-            b0[c] = XB_ADD(m, xb_logf_norm(sy));
-            g = XB_ADD(m, A[c]);
-        }
-        float wm = warp_max(g);
-        if (lane == 0) red[w] = wm;
-        __syncthreads();                                                        // B1
-        float gmax = red[0];
-#pragma unroll
-        for (int j = 1; j < W; j++) gmax = fmaxf(gmax, red[j]);
-        if (act) FS[c] = xb_expf_le0(XB_SUB(g, gmax));
-        __syncthreads();                                                        // B1b
-        // Thread c as DESTINATION state: numerators of its NZ incoming edges.
-        float x[NZ], s = 0.0f;
-        if (act) {
-#pragma unroll
-            for (int k = 0; k < NZ; k++) {
-                x[k] = XB_MUL(LP[c * NZ + k], FS[src[k]]);
-                s = (k == 0) ? x[k] : XB_ADD(s, x[k]);
-            }
-        }
-        s = warp_sum_tree(s);
-        if (lane == 0) red[W + w] = s;
-        __syncthreads();                                                        // B2
-        float tot = red[W];
-#pragma unroll
-        for (int j = 1; j < W; j++) tot = XB_ADD(tot, red[W + j]);
-        const float inv = XB_RCP(tot);
-        if (act) {
-#pragma unroll
-            for (int k = 0; k < NZ; k++) {
-                float p = XB_MUL(x[k], inv);
-                if (post_out) post_out[((size_t)t * N + n) * S + c * NZ + k] = p;
-                LP[c * NZ + k] = xb_logf_norm(XB_ADD(p, XB_POST_EPS));
-            }
-        }
-        __syncthreads();                                                        // B3
-        {
-            float2 *dst = reinterpret_cast<float2 *>(lp_out + ((size_t)t * N + n) * S) + c;
-            const float2 *srcv = reinterpret_cast<const float2 *>(LP) + c;
-            constexpr int NPAIR = S / 2, ROUNDS = (NPAIR + NT - 1) / NT;
-#pragma unroll
-            for (int k = 0; k < ROUNDS; k++)                 // unrolled on one base address each, immediate offsets
-                if ((k + 1) * NT <= NPAIR || k * NT + c < NPAIR) dst[k * NT] = srcv[k * NT];
-        }
-        if (act) {
-            float m = XB_ADD(LP[c * NZ], m1[c]);
-#pragma unroll
-            for (int j = 0; j < NB; j++) m = fmaxf(m, XB_ADD(LP[(cb + j) * NZ + kk], m1[cb + j]));
-            m0[c] = m;
-            bmax_out[((size_t)t * N + n) * C + c] = m;
-        }
-    }
-}
-
-// --------------------------------------------------------------------------------------------------
 // Forward sweep, Max semiring, over lp with the stored Max-beta: arg-max edge per step -> label
 // (edge % NZ), then path_to_str + left-pack for the row.   dynamic smem tail holds T labels.
 template <int NB, int SL>
@@ -411,10 +272,6 @@ template <int NB, int SL> size_t smem_bscan() {
     using L = Lat<NB, SL>;
     return sizeof(float) * (L::D * L::S + 2 * L::NT);
 }
-template <int NB, int SL> size_t smem_backward() {
-    using L = Lat<NB, SL>;
-    return sizeof(float) * (L::D * L::S + L::S + L::D * L::NT + 5 * L::NT + 2 * L::W);
-}
 template <int NB, int SL> size_t smem_vit(int T) {
     using L = Lat<NB, SL>;
     return sizeof(float) * (L::D * L::S + L::D * L::NT + 2 * L::NT + 4 * L::W + L::NT + 1) + ((T + 15) / 16) * 16;
@@ -436,15 +293,9 @@ int alpha_impl(xb_handle *h, const float *scores, int T, int N, float *alpha, fl
     return XB_OK;
 }
 template <int NB, int SL>
-int backward_impl(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
-                  float *post, float *beta, int mode, cudaStream_t s) {
+int backward_impl(xb_handle *h, const float *scores, int T, int N, float *bmax, float *beta, int mode, cudaStream_t s) {
     using L = Lat<NB, SL>;
-    if (mode == 0) {
-        auto k = crf_backward_kernel<NB, SL>;
-        size_t sm = smem_backward<NB, SL>();
-        if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, L::NT, sm, s>>>(scores, alpha, T, N, lp, bmax, post);
-    } else if (mode == 1) {
+    if (mode == 1) {
         auto k = crf_bscan_kernel<NB, SL, true>;
         size_t sm = smem_bscan<NB, SL>();
         if (int rc = set_smem(h, k, sm)) return rc;
@@ -493,12 +344,10 @@ int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alph
 #undef CALL
 }
 
-// mode 0: fused decode backward sweep (needs alpha; writes lp, bmax, optional post)
 // mode 1: Max-semiring backward scan of the raw scores into bmax;  mode 2: Log-semiring scan into beta
-int xb_decode_backward(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
-                       float *post, float *beta, int mode, cudaStream_t s) {
+int xb_decode_backward(xb_handle *h, const float *scores, int T, int N, float *bmax, float *beta, int mode, cudaStream_t s) {
     xb_stage_timer tm(h, XB_ST_CRF_BACKWARD, s);
-#define CALL(NB, SL) backward_impl<NB, SL>(h, scores, alpha, T, N, lp, bmax, post, beta, mode, s)
+#define CALL(NB, SL) backward_impl<NB, SL>(h, scores, T, N, bmax, beta, mode, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL
 }

@@ -30,6 +30,7 @@
 #include "xb_ptx.cuh"
 #include "xb_gemm.cuh"
 #include "xb_head_epilogue.cuh"
+#include "xb_exact_math.h"
 
 using namespace xbptx;
 
@@ -68,6 +69,7 @@ struct IPParams {
     int n_valid, ldo;         // valid output columns before expansion; output row pitch in elements
     int n_base, expand;       // IP_SCORES: blank score inserted in front of every n_base columns
     float scale, blank;
+    int exp_out;              // IP_SCORES: write E = xb_score_exp(score) (what the linear-domain decode consumes) instead of the score
     int no_prefetch;
     long long *dbg;           // optional (XB_INPROJ_DEBUG): stall cycles of the MMA thread of CTA 0: [acc_empty, full, issue, a_ready]
 };
@@ -300,18 +302,25 @@ inproj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ C
                     float v[BNI];
 #pragma unroll
                     for (int jj = 0; jj < BNI; jj++) v[jj] = p.scale * xbhead::fast_tanh(__uint_as_float(acc[jj]) + bs[jj]);
+                    // fused pipeline: hand the decode exp(score) -- the one exponential per edge its three sweeps would
+                    // otherwise each compute (bit-reproducible xb_score_exp, the decode contract's own function)
+                    if (p.exp_out) {
+#pragma unroll
+                        for (int jj = 0; jj < BNI; jj++) v[jj] = xb_score_exp(v[jj]);
+                    }
+                    const float blank = p.exp_out ? xb_score_exp(p.blank) : p.blank;
                     const uint32_t sr = smem_u32(S) + (uint32_t)(lane * RS * 4);
                     const int ncols = col_end - col0;
                     if (p.expand) {
                         const int nb = p.n_base, c = col0 / nb, e0 = col0 - c * nb;
                         const int pos0 = col0 + c + 1 - seg_start;         // staged position of column col0
                         if (ncols == BNI) {
-                            if (nb == 5) head_stage64<5, true>(v, sr, e0, pos0, ncols, p.blank);
-                            else if (nb == 4) head_stage64<4, true>(v, sr, e0, pos0, ncols, p.blank);
-                            else if (nb == 6) head_stage64<6, true>(v, sr, e0, pos0, ncols, p.blank);
-                            else head_stage64_dyn<true>(v, sr, nb, e0, pos0, ncols, p.blank);
+                            if (nb == 5) head_stage64<5, true>(v, sr, e0, pos0, ncols, blank);
+                            else if (nb == 4) head_stage64<4, true>(v, sr, e0, pos0, ncols, blank);
+                            else if (nb == 6) head_stage64<6, true>(v, sr, e0, pos0, ncols, blank);
+                            else head_stage64_dyn<true>(v, sr, nb, e0, pos0, ncols, blank);
                         } else {
-                            head_stage64_dyn<false>(v, sr, nb, e0, pos0, ncols, p.blank);
+                            head_stage64_dyn<false>(v, sr, nb, e0, pos0, ncols, blank);
                         }
                     } else {
 #pragma unroll
@@ -522,7 +531,7 @@ int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float 
 // CRF scores (M, ldo) fp32 = LinearCRFEncoder(x): the same A-stationary kernel with the head epilogue -- a CTA owns whole
 // output rows, W_head (<= 2 MB) streams from L2.  w_rows = rows of the zero-padded weight (multiple of 64, <= 3072).
 int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w_rows, const float *bias, int head_rows,
-                               float *scores, int ldo, int M, cudaStream_t s) {
+                               float *scores, int ldo, int M, int exp_out, cudaStream_t s) {
     XB_REQUIRE(h, w_rows % BNI == 0 && w_rows <= MAX_COLS && head_rows <= w_rows, "head of %d rows unsupported", head_rows);
     IPParams p = {};
     p.x = reinterpret_cast<const uint16_t *>(x);
@@ -532,5 +541,6 @@ int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w
     p.n_valid = head_rows; p.ldo = ldo;
     p.n_base = h->n_base; p.expand = h->expand_blanks;
     p.scale = h->scale; p.blank = h->blank_score;
+    p.exp_out = exp_out;
     return ip_launch<IP_SCORES>(h, w, w_rows, p, s);
 }

@@ -14,7 +14,7 @@ namespace {
 // one warp per read
 __global__ void stitch_kernel(const int8_t *__restrict__ rows, int T, const int32_t *__restrict__ chunk_first,
                               const int32_t *__restrict__ chunk_count, const int32_t *__restrict__ read_len, int n_reads,
-                              int chunksize, int overlap, int stride, int8_t *__restrict__ out, int out_stride,
+                              int chunksize, int overlap, int stride, int reverse, int8_t *__restrict__ out, int out_stride,
                               int32_t *__restrict__ out_len) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= n_reads) return;
@@ -25,12 +25,23 @@ __global__ void stitch_kernel(const int8_t *__restrict__ rows, int T, const int3
     const int first_end = stub > 0 ? (stub + semi) / stride : end;
     int8_t *o = out + (size_t)r * out_stride;
     int pos = 0;
-    for (int ci = 0; ci < nch; ci++) {
+    // reverse (util.py:180-184): chunks are walked backwards and every slice is taken from the END of its row with Python's
+    // negative indices: index -k resolves to T - k (clamped at 0), and -0 is 0 -- so `x[:-start]` is EMPTY when start == 0 and
+    // `x[-first_end:]` is the whole row when first_end == 0, exactly as the reference's expressions evaluate
+    auto neg = [T](int k) { return k == 0 ? 0 : max(T - k, 0); };
+    for (int step = 0; step < nch; step++) {
+        const int ci = reverse ? nch - 1 - step : step;
         int lo, hi;
         if (nch == 1) { lo = 0; hi = T; }
-        else if (ci == 0) { lo = 0; hi = first_end; }
-        else if (ci == nch - 1) { lo = start; hi = T; }
-        else { lo = start; hi = end; }
+        else if (!reverse) {
+            if (ci == 0) { lo = 0; hi = first_end; }
+            else if (ci == nch - 1) { lo = start; hi = T; }
+            else { lo = start; hi = end; }
+        } else {
+            if (ci == nch - 1) { lo = 0; hi = neg(start); }
+            else if (ci == 0) { lo = neg(first_end); hi = T; }
+            else { lo = neg(end); hi = neg(start); }
+        }
         lo = max(0, min(lo, T));
         hi = max(lo, min(hi, T));
         const int8_t *row = rows + (size_t)(first + ci) * T;
@@ -211,12 +222,12 @@ __global__ void ctc_simple_bwd_kernel(const float *__restrict__ scores, int T, i
 }  // namespace
 
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
-                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out,
+                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int reverse, int8_t *out,
                    int out_stride, int32_t *out_len, cudaStream_t s) {
     XB_REQUIRE(h, n_reads > 0 && chunksize > overlap && stride > 0, "bad stitch arguments");
     const int warps = 4;
     stitch_kernel<<<(n_reads + warps - 1) / warps, warps * 32, 0, s>>>(rows, T, chunk_first, chunk_count, read_len, n_reads,
-                                                                       chunksize, overlap, stride, out, out_stride, out_len);
+                                                                       chunksize, overlap, stride, reverse, out, out_stride, out_len);
     XB_LAUNCH_CHECK(h);
     return XB_OK;
 }

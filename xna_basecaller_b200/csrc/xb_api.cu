@@ -24,7 +24,7 @@ int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
 int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w_rows, const float *bias, int head_rows,
-                               float *scores, int ldo, int M, cudaStream_t s);
+                               float *scores, int ldo, int M, int exp_out, cudaStream_t s);
 int xb_preprocess_impl(xb_handle *h, const int16_t *raw, const int64_t *read_offset, const int32_t *read_len,
                        const double *scaling, const int32_t *offset, int n_reads, float *out, int32_t *out_len,
                        float *stats, cudaStream_t s);
@@ -34,7 +34,7 @@ int xb_ctc_loss_bwd_impl(xb_handle *h, const float *scores, int T, int N, const 
 int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
                      const int32_t *lengths, int normalise, float *loss, cudaStream_t s);
 int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
-                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out,
+                   const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int reverse, int8_t *out,
                    int out_stride, int32_t *out_len, cudaStream_t s);
 
 int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
@@ -193,9 +193,10 @@ int xb_create(xb_handle **out, int device, int max_N, int max_T, int n_base, int
     const size_t TN = (size_t)max_T * max_N, S = (size_t)h->C * h->NZ;
     int rc = XB_OK;
 #define TRY(x) if (rc == XB_OK) rc = (x)
-    TRY(dev_alloc(h, &h->alpha, (TN + max_N) * h->C));
-    TRY(dev_alloc(h, &h->bmax, (TN + max_N) * h->C));
-    TRY(dev_alloc(h, &h->lp, TN * S));
+    const size_t VP = (size_t)((h->C + 31) / 32) * 32 + 4;
+    TRY(dev_alloc(h, &h->alpha, (TN + max_N) * VP));
+    TRY(dev_alloc(h, &h->bmax, (TN + max_N) * VP));
+    TRY(dev_alloc(h, &h->lp, (TN + max_N) * VP));
     TRY(dev_alloc(h, &h->logz, (size_t)max_N));
     TRY(dev_alloc(h, &h->seq_dev, TN));
     TRY(dev_alloc(h, &h->lens_dev, (size_t)max_N));
@@ -422,7 +423,8 @@ int xb_lstm_stack_fwd(xb_handle *h, void *x_tnc, void *y_tnc, int T, int N, void
     return XB_OK;   // 5 layers: result landed in y_tnc
 }
 
-int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, void *stream) {
+// exp_out: write exp(score) (xb_score_exp) instead of the score -- the hand-over format of the fused host entry points
+static int head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, int exp_out, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
     if (!(h->loaded & 64)) return xb_fail(h, XB_ERR_STATE, "CRF head weights have not been loaded (xb_load_weights)");
     XB_REQUIRE(h, x_tnc && scores, "NULL buffer");
@@ -445,16 +447,43 @@ int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N
     }
 #endif
     return xb_head_astationary_launch(h, x_tnc, h->head_w, h->head_rows_padded, h->head_b, h->head_rows, scores,
-                                      h->expand_blanks ? h->C * h->NZ : h->head_rows, T * N, s);
+                                      h->expand_blanks ? h->C * h->NZ : h->head_rows, T * N, exp_out, s);
 }
 
-int xb_encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, void *stream) {
+int xb_crf_head_fwd(xb_handle *h, const void *x_tnc, float *scores, int T, int N, void *stream) {
+    return head_fwd(h, x_tnc, scores, T, N, 0, stream);
+}
+
+int xb_crf_head_fwd_exp(xb_handle *h, const void *x_tnc, float *escores, int T, int N, void *stream) {
+    if (h && !h->expand_blanks) return xb_fail(h, XB_ERR_STATE, "the exp hand-over format needs expand_blanks");
+    return head_fwd(h, x_tnc, escores, T, N, 1, stream);
+}
+
+static int encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, int exp_out, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
     XB_REQUIRE(h, L > 0 && L % XB_STRIDE == 0, "chunk length %d must be a positive multiple of the stride %d", L, XB_STRIDE);
     const int T = L / XB_STRIDE;
     if (int rc = xb_conv_stem_fwd(h, signal, sig_dtype, N, L, h->act0, stream)) return rc;
     if (int rc = xb_lstm_stack_fwd(h, h->act0, h->act1, T, N, stream)) return rc;
-    return xb_crf_head_fwd(h, h->act1, scores, T, N, stream);
+    return head_fwd(h, h->act1, scores, T, N, exp_out, stream);
+}
+
+int xb_encoder_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, void *stream) {
+    return encoder_fwd(h, signal, sig_dtype, N, L, scores, 0, stream);
+}
+
+// Fused encoder + decode of chunks that are already on the device: the head hands exp(scores) to the decode (h->scores
+// never holds log-domain scores on this route), labels / packed rows come back.  The *_host entry points and the read-set
+// pipeline run through here.
+int xb_basecall_chunks(xb_handle *h, const void *signal, int sig_dtype, int N, int L, int8_t *seq, int8_t *qstring,
+                       int32_t *lens, void *stream) {
+    if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
+    XB_REQUIRE(h, signal && seq && lens, "NULL buffer");
+    if (!h->scores) return xb_fail(h, XB_ERR_STATE, "handle was created without the encoder");
+    XB_REQUIRE(h, h->expand_blanks, "the fused route needs expand_blanks (Viterbi decode over C*NZ scores)");
+    if (int rc = encoder_fwd(h, signal, sig_dtype, N, L, h->scores, 1, stream)) return rc;
+    return xb_decode_lin(h, h->scores, 1, L / XB_STRIDE, N, nullptr, seq, qstring, lens, nullptr,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ CRF
@@ -479,20 +508,19 @@ int xb_crf_forward_scores(xb_handle *h, const float *scores, int T, int N, float
 int xb_crf_backward_scores(xb_handle *h, const float *scores, int T, int N, float *beta, void *stream) {
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, beta != nullptr, "beta is NULL");
-    return xb_decode_backward(h, scores, nullptr, T, N, nullptr, nullptr, nullptr, beta, 2, s);
+    return xb_decode_backward(h, scores, T, N, nullptr, beta, 2, s);
 }
 
 int xb_crf_posteriors(xb_handle *h, const float *scores, int T, int N, float *post, void *stream) {
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, post != nullptr, "post is NULL");
-    if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, nullptr, s)) return rc;
-    return xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, post, nullptr, 0, s);
+    return xb_decode_lin(h, scores, 0, T, N, nullptr, nullptr, nullptr, nullptr, post, s);
 }
 
 int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labels_nt, void *stream) {
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, labels_nt != nullptr, "labels is NULL");
-    if (int rc = xb_decode_backward(h, scores, nullptr, T, N, nullptr, h->bmax, nullptr, nullptr, 1, s)) return rc;
+    if (int rc = xb_decode_backward(h, scores, T, N, h->bmax, nullptr, 1, s)) return rc;
     return xb_decode_viterbi_fwd(h, scores, h->bmax, T, N, labels_nt, nullptr, nullptr, nullptr, s);
 }
 
@@ -500,9 +528,14 @@ int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, 
                   int8_t *labels_nt, float *post, void *stream) {
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, seq != nullptr && lens != nullptr, "seq / lens is NULL");
-    if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, nullptr, s)) return rc;
-    if (int rc = xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, post, nullptr, 0, s)) return rc;
-    return xb_decode_viterbi_fwd(h, h->lp, h->bmax, T, N, labels_nt, seq, qstring, lens, s);
+    return xb_decode_lin(h, scores, 0, T, N, labels_nt, seq, qstring, lens, post, s);
+}
+
+int xb_crf_decode_exp(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring, int32_t *lens,
+                      int8_t *labels_nt, float *post, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, seq != nullptr && lens != nullptr, "seq / lens is NULL");
+    return xb_decode_lin(h, scores, 1, T, N, labels_nt, seq, qstring, lens, post, s);
 }
 
 int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets, int Lmax,
@@ -518,19 +551,19 @@ int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const i
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, targets && lengths && grad_loss && alpha_ws && grad_scores, "NULL buffer");
     if (normalise) {       // logZ (for the shift) and the posteriors of the full lattice, straight into grad_scores
-        if (int rc = xb_decode_alpha(h, scores, T, N, h->alpha, h->logz, s)) return rc;
-        if (int rc = xb_decode_backward(h, scores, h->alpha, T, N, h->lp, h->bmax, grad_scores, nullptr, 0, s)) return rc;
+        if (int rc = xb_decode_lin(h, scores, 0, T, N, nullptr, nullptr, nullptr, nullptr, grad_scores, s)) return rc;
+        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, s)) return rc;
     }
     return xb_ctc_loss_bwd_impl(h, scores, T, N, targets, Lmax, lengths, normalise, grad_loss, alpha_ws, grad_scores, s);
 }
 
 int xb_stitch(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk_first, const int32_t *chunk_count,
-              const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int8_t *out, int out_stride,
-              int32_t *out_len, void *stream) {
+              const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int reverse, int8_t *out,
+              int out_stride, int32_t *out_len, void *stream) {
     if (!h) return xb_fail(nullptr, XB_ERR_ARG, "NULL handle");
     XB_REQUIRE(h, rows && chunk_first && chunk_count && read_len && out && out_len, "NULL buffer");
     XB_CUDA(h, cudaSetDevice(h->device));
-    return xb_stitch_impl(h, rows, T, chunk_first, chunk_count, read_len, n_reads, chunksize, overlap, stride, out,
+    return xb_stitch_impl(h, rows, T, chunk_first, chunk_count, read_len, n_reads, chunksize, overlap, stride, reverse, out,
                           out_stride, out_len, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -562,8 +595,7 @@ int xb_compute_scores_host(xb_handle *h, const float *signal_host, int N, int L,
     if (int rc = check_tn(h, T, N)) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     XB_CUDA(h, cudaMemcpyAsync(h->signal_dev, signal_host, (size_t)N * L * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (int rc = xb_encoder_fwd(h, h->signal_dev, XB_SIG_F32, N, L, h->scores, stream)) return rc;
-    if (int rc = xb_crf_decode(h, h->scores, T, N, h->seq_dev, nullptr, h->lens_dev, nullptr, nullptr, stream)) return rc;
+    if (int rc = xb_basecall_chunks(h, h->signal_dev, XB_SIG_F32, N, L, h->seq_dev, nullptr, h->lens_dev, stream)) return rc;
     XB_CUDA(h, cudaMemcpyAsync(seq_host, h->seq_dev, (size_t)N * T, cudaMemcpyDeviceToHost, s));
     XB_CUDA(h, cudaMemcpyAsync(lens_host, h->lens_dev, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     XB_CUDA(h, cudaStreamSynchronize(s));
@@ -612,9 +644,9 @@ int xb_compute_scores_submit(xb_handle *h, int slot, const float *signal_host, i
     XB_CUDA(h, cudaMemcpyAsync(sig, signal_host, (size_t)N * L * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
     XB_CUDA(h, cudaEventRecord(h->ev_h2d[slot], h->h2d_stream));
     XB_CUDA(h, cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
-    if (int rc = xb_encoder_fwd(h, sig, XB_SIG_F32, N, L, h->scores, stream)) return rc;
+    if (int rc = encoder_fwd(h, sig, XB_SIG_F32, N, L, h->scores, 1, stream)) return rc;
     XB_CUDA(h, cudaEventRecord(h->ev_enc[slot], s));
-    if (int rc = xb_crf_decode(h, h->scores, T, N, seq, nullptr, lens, nullptr, nullptr, stream)) return rc;
+    if (int rc = xb_decode_lin(h, h->scores, 1, T, N, nullptr, seq, nullptr, lens, nullptr, s)) return rc;
     XB_CUDA(h, cudaEventRecord(h->ev_dec[slot], s));
     XB_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_dec[slot], 0));
     XB_CUDA(h, cudaMemcpyAsync(seq_host, seq, (size_t)N * T, cudaMemcpyDeviceToHost, h->d2h_stream));

@@ -77,9 +77,11 @@ struct xb_handle {
     bool slot_used[2] = {false, false};
 
     // decode workspace
-    float *alpha = nullptr;      // (max_T+1, max_N, C)
-    float *bmax = nullptr;       // (max_T+1, max_N, C)
-    float *lp = nullptr;         // (max_T, max_N, C*NZ)
+    // three (max_T+1, max_N, VP) state-vector buffers, VP = round_up(C, 32) + 4 floats (16-byte aligned rows for the
+    // bulk-copy ring of crf_decode_lin.cu: a_hat, bm_hat, b_hat); the log-domain scans use alpha / bmax with pitch C
+    float *alpha = nullptr;
+    float *bmax = nullptr;
+    float *lp = nullptr;
     float *logz = nullptr;       // (max_N)
     float *ctc_ws = nullptr;
     int *lstm_counters = nullptr; // per-group step counters of the persistent LSTM kernel
@@ -160,7 +162,9 @@ template <> struct xb16<true> {
 
 // ---- entry points implemented in the other translation units ------------------------------------
 int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s);
-int xb_decode_backward(xb_handle *h, const float *scores, const float *alpha, int T, int N, float *lp, float *bmax,
-                       float *post, float *beta, int mode, cudaStream_t s);
+int xb_decode_backward(xb_handle *h, const float *scores, int T, int N, float *bmax, float *beta, int mode, cudaStream_t s);
+int xb_decode_lin(xb_handle *h, const float *scores, int lin_input, int T, int N, int8_t *labels, int8_t *seq, int8_t *qs,
+                  int32_t *lens, float *post, cudaStream_t s);
+int xb_score_exp_launch(xb_handle *h, const float *in, float *out, size_t n, cudaStream_t s);
 int xb_decode_viterbi_fwd(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels,
                           int8_t *seq, int8_t *qstring, int32_t *lens, cudaStream_t s);

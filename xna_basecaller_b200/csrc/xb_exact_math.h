@@ -129,6 +129,39 @@ XB_HD float xb_expf_le0(float x) {
     return (x >= -86.0f) ? v : 0.0f;
 }
 
+// xb_expf on the clamped score domain [-80, 80] of the linear-domain decode: no overflow / underflow guards at all.
+XB_HD float xb_expf_mid(float x) {
+    const float magic = 12582912.0f;
+    float t = XB_FMA(x, 1.44269504088896341f, magic);
+    float n = XB_SUB(t, magic);
+    float r = XB_FMA(n, -0.693359375f, x);
+    r = XB_FMA(n, 2.12194440e-4f, r);
+    float z = XB_MUL(r, r);
+    float p = 1.9875691500e-4f;
+    p = XB_FMA(p, r, 1.3981999507e-3f);
+    p = XB_FMA(p, r, 8.3334519073e-3f);
+    p = XB_FMA(p, r, 4.1665795894e-2f);
+    p = XB_FMA(p, r, 1.6666665459e-1f);
+    p = XB_FMA(p, r, 5.0000001201e-1f);
+    p = XB_FMA(p, z, r);
+    p = XB_ADD(p, 1.0f);
+    uint32_t ni = XB_F2U(t) - 0x4b400000u;
+    return XB_U2F(XB_F2U(p) + (ni << 23));
+}
+// exp of a CRF score as the linear-domain decode defines it: clamp to [-80, 80], then xb_expf_mid
+XB_HD float xb_score_exp(float m) {
+    m = m < -80.0f ? -80.0f : (m > 80.0f ? 80.0f : m);
+    return xb_expf_mid(m);
+}
+// power-of-two rescaling factor of a non-negative state vector with maximum mx: 2^(127 - biased exponent), so that
+// mx * scale lies in [1, 2); 1 for zero / subnormal / inf / nan.  Exact (no rounding) on both sides.
+XB_HD float xb_pow2_scale(float mx) {
+    uint32_t b = XB_F2U(mx);
+    uint32_t e = (b >> 23) & 0xffu;
+    if (e == 0u || e == 255u || (b >> 31)) return 1.0f;
+    return XB_U2F((254u - e) << 23);
+}
+
 XB_HD float xb_logf_norm(float x) {
     uint32_t iy = XB_F2U(x) - 0x3f3504f3u;
     int32_t e = (int32_t)iy >> 23;
