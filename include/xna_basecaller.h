@@ -48,7 +48,8 @@ enum xb_status {
 
 enum xb_flags {
     XB_FLAG_BF16 = 1,            /* weights rounded to bfloat16 (activations stay float16)     */
-    XB_FLAG_NO_ENCODER = 2       /* decode-only handle: no encoder workspace is allocated      */
+    XB_FLAG_NO_ENCODER = 2,      /* decode-only handle: no encoder workspace is allocated      */
+    XB_FLAG_TRAIN = 8            /* keep transposed bf16 weight copies for xb_encoder_bwd      */
     /* (4 was the one-launch-per-step LSTM of round 1; it exists only in -DXB_EXPERIMENTS builds) */
 };
 
@@ -113,6 +114,18 @@ int xb_crf_logz(xb_handle *h, const float *scores, int T, int N, float *logz, vo
 int xb_crf_forward_scores(xb_handle *h, const float *scores, int T, int N, float *alpha, void *stream);
 int xb_crf_backward_scores(xb_handle *h, const float *scores, int T, int N, float *beta, void *stream);
 
+/* The same three with the semiring argument the reference's methods take (S: semiring = Log, crf/model.py:41,51,57):
+ * XB_SEMIRING_MAX gives the best path's score / the Max-semiring forward and backward vectors. */
+enum xb_semiring { XB_SEMIRING_LOG = 0, XB_SEMIRING_MAX = 1 };
+int xb_crf_logz_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *logz, void *stream);
+int xb_crf_forward_scores_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *alpha, void *stream);
+int xb_crf_backward_scores_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *beta, void *stream);
+
+/* SequenceDist.posteriors(scores, Max) (what CTC_CRF.viterbi arg-maxes, crf/model.py:92-95): the one-hot tensor at the
+ * arg-max edge of every step's max-marginals (first flat index c*NZ + k on ties).  edges_nt (N, T) int32 receives the
+ * edge indices; post (T, N, C*NZ) fp32 the one-hot tensor itself, may be NULL. */
+int xb_crf_posteriors_max(xb_handle *h, const float *scores, int T, int N, int32_t *edges_nt, float *post, void *stream);
+
 /* SequenceDist.posteriors(scores, Log) (crf/model.py:216): post (T, N, C*NZ) fp32. */
 int xb_crf_posteriors(xb_handle *h, const float *scores, int T, int N, float *post, void *stream);
 
@@ -155,6 +168,18 @@ int xb_ctc_crf_loss_fwd(xb_handle *h, const float *scores, int T, int N, const i
 int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const int32_t *targets,
                         int Lmax, const int32_t *lengths, int normalise, const float *grad_loss,
                         float *alpha_ws, float *grad_scores, void *stream);
+
+/* The encoder half of Trainer.train_one_step (training.py:91-117) on a handle created with XB_FLAG_TRAIN:
+ *   xb_encoder_fwd_train  = scores_ = model(data_): xb_encoder_fwd that also keeps the layer inputs and the LSTM gate /
+ *                           cell values of every step in handle workspace (N must be a multiple of 8);
+ *   xb_encoder_bwd        = what loss.backward() does below the scores: dscores (T,N,C*NZ) fp32 (from
+ *                           xb_ctc_crf_loss_bwd) -> fp32 gradients of the XB_NUM_WEIGHTS parameter tensors, in
+ *                           xb_load_weights' order and the reference's layouts -- except encoder.2.conv.weight, whose
+ *                           gradient is (768, 320) = [out][tap*16 + in] (the caller reshapes to (768,16,19)).
+ * signal and scores are the buffers of the matching forward call. */
+int xb_encoder_fwd_train(xb_handle *h, const void *signal, int sig_dtype, int N, int L, float *scores, void *stream);
+int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float *scores, const float *dscores,
+                   float *const *grads, int n_tensors, void *stream);
 
 /* util.stitch over left-packed chunks (util.py:169-188; crf/basecall.py:15-24): for each read r,
  * concatenates slices of its chunks' packed rows.  chunk_first[r], chunk_count[r], read_len[r]

@@ -128,6 +128,29 @@ def test_exp_hand_over_format(handles, n_base, T, N):
 
 
 @pytest.mark.parametrize('n_base', [4, 5, 6])
+def test_max_semiring_methods(handles, n_base):
+    """CTC_CRF.logZ / forward_scores / backward_scores / posteriors with S = Max (crf/model.py:41-61, 92-95) through the
+    plugin class against the torch restatement: max-plus arithmetic is exact, so values agree to rounding of the same
+    additions and the one-hot posteriors agree exactly."""
+    from xna_basecaller_b200.crf.model import CTC_CRF, Max
+    s = synthetic_scores(31 + n_base, 150, 4, n_base)
+    ref = bo.CRF(3, ALPHABETS[n_base])
+    sd = CTC_CRF(3, ALPHABETS[n_base])
+    sc = s.cuda()
+    np.testing.assert_allclose(sd.logZ(sc, Max).cpu().numpy(), ref.logZ(s, 'max').numpy(), rtol=1e-6)
+    np.testing.assert_allclose(sd.forward_scores(sc, Max).cpu().numpy(), ref.forward_scores(s, 'max').numpy(), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(sd.backward_scores(sc, Max).cpu().numpy(), ref.backward_scores(s, 'max').numpy(), rtol=1e-6, atol=1e-4)
+    post = sd.posteriors(sc, Max).cpu()
+    want = ref.posteriors(s, 'max')
+    assert post.sum(2).eq(1).all() and (post.eq(0) | post.eq(1)).all()
+    assert (post.argmax(2) == want.argmax(2)).float().mean().item() > 0.999        # ties in fp32 sums aside: identical
+    assert torch.equal(post.argmax(2) % (n_base + 1), sd.viterbi(sc).cpu())
+    with pytest.raises(NotImplementedError):
+        sd.logZ(sc, 'tropical')
+    sd.engine.close()
+
+
+@pytest.mark.parametrize('n_base', [4, 5, 6])
 def test_ctc_loss_matches_reference_golden(handles, golden, n_base):
     h = handles[n_base]
     g = golden['crf']

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libxna_b200.so')
 
 XB_FLAG_BF16 = 1
 XB_FLAG_NO_ENCODER = 2
+XB_FLAG_TRAIN = 8
 XB_SIG_F32, XB_SIG_F16, XB_SIG_I16 = 0, 1, 2
 NUM_WEIGHTS = 28
 
@@ -24,6 +25,8 @@ SYMBOLS = (
     'xb_crf_forward_scores', 'xb_crf_backward_scores', 'xb_crf_posteriors', 'xb_crf_viterbi', 'xb_crf_decode',
     'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_compute_scores_submit', 'xb_compute_scores_wait', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times', 'xb_crf_head_fwd_exp', 'xb_crf_decode_exp', 'xb_basecall_chunks',
+    'xb_crf_logz_s', 'xb_crf_forward_scores_s', 'xb_crf_backward_scores_s', 'xb_crf_posteriors_max',
+    'xb_encoder_fwd_train', 'xb_encoder_bwd',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
           'crf_backward', 'crf_viterbi')
@@ -60,6 +63,12 @@ def load():
     lib.xb_crf_forward_scores.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_backward_scores.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_posteriors.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.xb_encoder_fwd_train.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_encoder_bwd.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(vp), ci, vp]
+    lib.xb_crf_logz_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_crf_forward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_crf_backward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.xb_crf_posteriors_max.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     lib.xb_crf_viterbi.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_crf_decode.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.xb_crf_decode_exp.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
@@ -97,7 +106,7 @@ class Handle:
     """One xb_handle: a device, an alphabet, capacity (max_N chunks x max_T steps) and, after
     load_weights(), the repacked encoder weights."""
 
-    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True):
+    def __init__(self, alphabet, state_len=3, max_N=64, max_T=800, device=0, bf16=False, encoder=True, train=False):
         if not torch.cuda.is_available():
             raise RuntimeError('xna_basecaller_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = load()
@@ -110,7 +119,8 @@ class Handle:
         self.device = torch.device('cuda', device) if not isinstance(device, torch.device) else device
         self.bf16 = bf16
         self.dtype16 = torch.float16        # activations are fp16 in both modes; bf16 rounds the WEIGHTS to bfloat16
-        flags = (XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER)
+        flags = (XB_FLAG_BF16 if bf16 else 0) | (0 if encoder else XB_FLAG_NO_ENCODER) | (XB_FLAG_TRAIN if train else 0)
+        self.train = train
         h = ctypes.c_void_p()
         rc = self.lib.xb_create(ctypes.byref(h), self.device.index or 0, max_N, max_T, self.n_base, state_len,
                                 self.alphabet.encode(), flags)
@@ -253,6 +263,38 @@ class Handle:
                     'xb_encoder_fwd')
         return scores
 
+    # ------------------------------------------------------------------ training step (handle created with train=True)
+    WEIGHT_KEYS = (['encoder.%d.conv.%s' % (i, k) for i in range(3) for k in ('weight', 'bias')] +
+                   ['encoder.%d.rnn.%s' % (i, k) for i in range(4, 9)
+                    for k in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')] +
+                   ['encoder.9.linear.weight', 'encoder.9.linear.bias'])
+
+    def encoder_train(self, signal):
+        """Training forward: scores (T, N, C*NZ) fp32; the handle keeps what encoder_backward needs."""
+        signal, code = self._sig(signal.to(self.device))
+        N, L = signal.shape
+        scores = torch.empty(L // 5, N, self.C * self.NZ, dtype=torch.float32, device=self.device)
+        self._check(self.lib.xb_encoder_fwd_train(self.h, _ptr(signal), code, N, L, _ptr(scores), _stream(self.device)),
+                    'xb_encoder_fwd_train')
+        self._train_keep = (signal, code, scores)
+        return scores
+
+    def encoder_backward(self, dscores):
+        """dscores (T, N, C*NZ) fp32 -> {reference state_dict key: fp32 gradient in the reference's layout}."""
+        signal, code, scores = self._train_keep
+        ds = dscores.to(self.device, torch.float32).contiguous()
+        head_rows = self.C * self.n_base
+        shapes = [(4, 1, 5), (4,), (16, 4, 5), (16,), (768, 320), (768,)]
+        for _ in range(5):
+            shapes += [(3072, 768), (3072, 768), (3072,), (3072,)]
+        shapes += [(head_rows, 768), (head_rows,)]
+        grads = [torch.zeros(*s, dtype=torch.float32, device=self.device) for s in shapes]
+        arr = (ctypes.c_void_p * NUM_WEIGHTS)(*[g.data_ptr() for g in grads])
+        self._check(self.lib.xb_encoder_bwd(self.h, _ptr(signal), code, _ptr(scores), _ptr(ds), arr, NUM_WEIGHTS,
+                                            _stream(self.device)), 'xb_encoder_bwd')
+        grads[4] = grads[4][:, :304].reshape(768, 19, 16).permute(0, 2, 1).contiguous()      # [out][tap][in] -> (768, 16, 19)
+        return dict(zip(self.WEIGHT_KEYS, grads))
+
     # ------------------------------------------------------------------ CRF
     def _scores(self, scores):
         s = scores.to(self.device, torch.float32).contiguous()
@@ -261,25 +303,35 @@ class Handle:
             raise ValueError('scores last dim %d != C*NZ = %d' % (W, self.C * self.NZ))
         return s, T, N
 
-    def logZ(self, scores):
+    def logZ(self, scores, semiring=0):
+        """semiring 0 = Log (logsumexp over paths), 1 = Max (score of the best path)."""
         s, T, N = self._scores(scores)
         out = torch.empty(N, dtype=torch.float32, device=self.device)
-        self._check(self.lib.xb_crf_logz(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)), 'xb_crf_logz')
+        self._check(self.lib.xb_crf_logz_s(self.h, _ptr(s), T, N, int(semiring), _ptr(out), _stream(self.device)), 'xb_crf_logz_s')
         return out
 
-    def forward_scores(self, scores):
+    def forward_scores(self, scores, semiring=0):
         s, T, N = self._scores(scores)
         out = torch.empty(T + 1, N, self.C, dtype=torch.float32, device=self.device)
-        self._check(self.lib.xb_crf_forward_scores(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)),
-                    'xb_crf_forward_scores')
+        self._check(self.lib.xb_crf_forward_scores_s(self.h, _ptr(s), T, N, int(semiring), _ptr(out), _stream(self.device)),
+                    'xb_crf_forward_scores_s')
         return out
 
-    def backward_scores(self, scores):
+    def backward_scores(self, scores, semiring=0):
         s, T, N = self._scores(scores)
         out = torch.empty(T + 1, N, self.C, dtype=torch.float32, device=self.device)
-        self._check(self.lib.xb_crf_backward_scores(self.h, _ptr(s), T, N, _ptr(out), _stream(self.device)),
-                    'xb_crf_backward_scores')
+        self._check(self.lib.xb_crf_backward_scores_s(self.h, _ptr(s), T, N, int(semiring), _ptr(out), _stream(self.device)),
+                    'xb_crf_backward_scores_s')
         return out
+
+    def posteriors_max(self, scores, want_onehot=True):
+        """posteriors(scores, Max): (edges (N, T) int32 flat arg-max edge index per step, one-hot (T, N, C*NZ) | None)."""
+        s, T, N = self._scores(scores)
+        edges = torch.empty(N, T, dtype=torch.int32, device=self.device)
+        post = torch.empty_like(s) if want_onehot else None
+        self._check(self.lib.xb_crf_posteriors_max(self.h, _ptr(s), T, N, _ptr(edges), _ptr(post), _stream(self.device)),
+                    'xb_crf_posteriors_max')
+        return edges, post
 
     def posteriors(self, scores):
         s, T, N = self._scores(scores)

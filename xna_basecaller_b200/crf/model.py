@@ -75,28 +75,33 @@ class CTC_CRF:
                                encoder=False)
 
     @staticmethod
-    def _only_log(S, what):
-        if S is not Log and getattr(S, '__name__', '') != 'Log':
-            raise NotImplementedError('%s is implemented for the Log semiring (use viterbi() for Max)' % what)
+    def _semiring(S):
+        """0 = Log, 1 = Max; accepts this module's markers, seqdist's semiring objects or their names."""
+        name = S if isinstance(S, str) else getattr(S, '__name__', getattr(S, 'name', type(S).__name__))
+        name = str(name).lower()
+        if S is Log or name == 'log':
+            return 0
+        if S is Max or name == 'max':
+            return 1
+        raise NotImplementedError('semiring %r: the CUDA scans implement Log and Max' % (S,))
 
     def logZ(self, scores, S=Log):
-        self._only_log(S, 'logZ')
-        return self._handle(scores).logZ(scores)
+        return self._handle(scores).logZ(scores, self._semiring(S))
 
     def normalise(self, scores):
         return scores - self.logZ(scores)[:, None] / len(scores)
 
     def forward_scores(self, scores, S=Log):
-        self._only_log(S, 'forward_scores')
-        return self._handle(scores).forward_scores(scores)
+        return self._handle(scores).forward_scores(scores, self._semiring(S))
 
     def backward_scores(self, scores, S=Log):
-        self._only_log(S, 'backward_scores')
-        return self._handle(scores).backward_scores(scores)
+        return self._handle(scores).backward_scores(scores, self._semiring(S))
 
     def posteriors(self, scores, S=Log):
-        """Edge posteriors d(sum logZ)/d scores, (T, N, C*NZ) fp32 (seqdist.core.SequenceDist.posteriors)."""
-        self._only_log(S, 'posteriors')
+        """Edge posteriors d(sum logZ_S)/d scores, (T, N, C*NZ) fp32 (seqdist.core.SequenceDist.posteriors): the softmax
+        over all edges of a step for Log, the one-hot at the arg-max edge of the max-marginals for Max."""
+        if self._semiring(S) == 1:
+            return self._handle(scores).posteriors_max(scores)[1]
         return self._handle(scores).posteriors(scores)
 
     def viterbi(self, scores):

@@ -22,8 +22,8 @@ using namespace xbcrf;
 namespace {
 
 // --------------------------------------------------------------------------------------------------
-// Forward sweep, Log semiring: alpha (T+1,N,C) and / or logZ (N).      grid = N, block = NT
-template <int NB, int SL>
+// Forward sweep, Log or Max semiring: alpha (T+1,N,C) and / or logZ (N).      grid = N, block = NT
+template <int NB, int SL, bool USE_MAX>
 __global__ void __launch_bounds__(Lat<NB, SL>::NT)
 crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restrict__ alpha_out,
                  float *__restrict__ logz_out) {
@@ -73,7 +73,7 @@ crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restri
                 x[k] = XB_ADD(M[k], ac[src[k]]);
                 m = (k == 0) ? x[k] : fmaxf(m, x[k]);
             }
-            float v = lse_exact<NZ>(x, m);
+            float v = USE_MAX ? m : lse_exact<NZ>(x, m);
             an[c] = v;
             if (aout) *aout = v;
         }
@@ -95,7 +95,7 @@ crf_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restri
         if (c == 0) {
             float s = red[W];
             for (int i = 1; i < W; i++) s = XB_ADD(s, red[W + i]);
-            logz_out[n] = XB_ADD(m, xb_logf(s));
+            logz_out[n] = USE_MAX ? m : XB_ADD(m, xb_logf(s));        // Max semiring: the best path's score
         }
     }
 }
@@ -158,7 +158,8 @@ template <int NB, int SL>
 __global__ void __launch_bounds__(Lat<NB, SL>::NT)
 crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ bmax, int T, int N,
                        int8_t *__restrict__ labels_out, int8_t *__restrict__ seq_out,
-                       int8_t *__restrict__ qs_out, int32_t *__restrict__ lens_out, Alphabet abc) {
+                       int8_t *__restrict__ qs_out, int32_t *__restrict__ lens_out, int32_t *__restrict__ edges_out,
+                       Alphabet abc) {
     using L = Lat<NB, SL>;
     constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
     extern __shared__ __align__(16) float smem[];
@@ -215,6 +216,7 @@ crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ b
                 if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
             }
             lab[t - 1] = (int8_t)(bi % NZ);
+            if (edges_out) edges_out[(size_t)n * T + t - 1] = bi;
         }
         const float *M = ring + (t % D) * S + c * NZ;
         const float *ac = am + (t & 1) * NT;
@@ -258,6 +260,7 @@ crf_viterbi_fwd_kernel(const float *__restrict__ lp, const float *__restrict__ b
             if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
         }
         lab[T - 1] = (int8_t)(bi % NZ);
+        if (edges_out) edges_out[(size_t)n * T + T - 1] = bi;
     }
     __syncthreads();
 
@@ -283,12 +286,18 @@ template <typename K> int set_smem(xb_handle *h, K kernel, size_t bytes) {
 }
 
 template <int NB, int SL>
-int alpha_impl(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s) {
+int alpha_impl(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, int use_max, cudaStream_t s) {
     using L = Lat<NB, SL>;
-    auto k = crf_alpha_kernel<NB, SL>;
     size_t sm = smem_alpha<NB, SL>();
-    if (int rc = set_smem(h, k, sm)) return rc;
-    k<<<N, L::NT, sm, s>>>(scores, T, N, alpha, logz);
+    if (use_max) {
+        auto k = crf_alpha_kernel<NB, SL, true>;
+        if (int rc = set_smem(h, k, sm)) return rc;
+        k<<<N, L::NT, sm, s>>>(scores, T, N, alpha, logz);
+    } else {
+        auto k = crf_alpha_kernel<NB, SL, false>;
+        if (int rc = set_smem(h, k, sm)) return rc;
+        k<<<N, L::NT, sm, s>>>(scores, T, N, alpha, logz);
+    }
     XB_LAUNCH_CHECK(h);
     return XB_OK;
 }
@@ -311,14 +320,14 @@ int backward_impl(xb_handle *h, const float *scores, int T, int N, float *bmax, 
 }
 template <int NB, int SL>
 int vit_impl(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels, int8_t *seq,
-             int8_t *qs, int32_t *lens, cudaStream_t s) {
+             int8_t *qs, int32_t *lens, int32_t *edges, cudaStream_t s) {
     using L = Lat<NB, SL>;
     auto k = crf_viterbi_fwd_kernel<NB, SL>;
     size_t sm = smem_vit<NB, SL>(T);
     if (int rc = set_smem(h, k, sm)) return rc;
     Alphabet abc;
     for (int i = 0; i < 16; i++) abc.ch[i] = h->alphabet[i];
-    k<<<N, L::NT, sm, s>>>(lp, bmax, T, N, labels, seq, qs, lens, abc);
+    k<<<N, L::NT, sm, s>>>(lp, bmax, T, N, labels, seq, qs, lens, edges, abc);
     XB_LAUNCH_CHECK(h);
     return XB_OK;
 }
@@ -337,9 +346,9 @@ int vit_impl(xb_handle *h, const float *lp, const float *bmax, int T, int N, int
 
 }  // namespace
 
-int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s) {
+int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, int use_max, cudaStream_t s) {
     xb_stage_timer tm(h, XB_ST_CRF_ALPHA, s);
-#define CALL(NB, SL) alpha_impl<NB, SL>(h, scores, T, N, alpha, logz, s)
+#define CALL(NB, SL) alpha_impl<NB, SL>(h, scores, T, N, alpha, logz, use_max, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL
 }
@@ -353,9 +362,9 @@ int xb_decode_backward(xb_handle *h, const float *scores, int T, int N, float *b
 }
 
 int xb_decode_viterbi_fwd(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels,
-                          int8_t *seq, int8_t *qstring, int32_t *lens, cudaStream_t s) {
+                          int8_t *seq, int8_t *qstring, int32_t *lens, int32_t *edges, cudaStream_t s) {
     xb_stage_timer tm(h, XB_ST_CRF_VITERBI, s);
-#define CALL(NB, SL) vit_impl<NB, SL>(h, lp, bmax, T, N, labels, seq, qstring, lens, s)
+#define CALL(NB, SL) vit_impl<NB, SL>(h, lp, bmax, T, N, labels, seq, qstring, lens, edges, s)
     XB_LATTICE_DISPATCH(h, CALL)
 #undef CALL
 }

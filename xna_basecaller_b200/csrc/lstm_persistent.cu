@@ -88,6 +88,7 @@ struct PLParams {
     int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
     int prefetch_y;             // d > 0: prefetch the y rows of step s+d into L2
     long long *dbg;             // optional timeline (XB_EXPERIMENTS, XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
+    uint16_t *save;             // training forward (SAVE kernels): (T, N, 5, 768) fp16 = activated i, f, g, o and the cell state c
 };
 
 #ifdef XB_EXPERIMENTS
@@ -129,7 +130,7 @@ template <> __device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, u
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
-template <bool BF16, int SUB, int NS, int EW, int GB>
+template <bool BF16, int SUB, int NS, int EW, int GB, bool SAVE = false>
 __global__ void __launch_bounds__(Cfg<SUB, NS, EW, GB>::THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
     using X = xb16<BF16>;
@@ -339,6 +340,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             // phase B: c' = sig(f) c + sig(i) tanh(g), h = sig(o) tanh(c'), written stage by stage over all cells so
             // that the MUFU latencies overlap.
             float hout[CELLS];
+            float sv[SAVE ? 5 : 1][CELLS];           // training forward: what BPTT needs of this step
 #if XB_LSTM_MUFU_TANH
             // Five MUFU.TANH per cell (sigmoid(x) = 0.5 tanh(0.5 x) + 0.5) and a dozen FMAs: a third of the instructions
             // of the exp/rcp form below.  tanh.approx.f32 has ~2^-11 relative error, the size of the fp16 rounding of h.
@@ -351,6 +353,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                 const float cn = fmaf(sf, cst[i], si * tg);
                 cst[i] = cn;
                 hout[i] = so * tanh_approx(cn);
+                if (SAVE) { sv[0][i] = si; sv[SAVE ? 1 : 0][i] = sf; sv[SAVE ? 2 : 0][i] = tg; sv[SAVE ? 3 : 0][i] = so; sv[SAVE ? 4 : 0][i] = cn; }
             }
 #else
             // Seven MUFU ops per cell: the four gate activations share one reciprocal (1/(d_i d_f d_g d_o) times the
@@ -406,6 +409,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             if (lane < NC && col0 + lane < cnt)
                 *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
                     lds_v4(st_s + 2u * (lane * ST_PITCH));
+            if (SAVE) {       // i, f, g, o, c of the step through the same staging rows: (T, N, 5, 768) fp16
+#pragma unroll
+                for (int qn = 0; qn < 5; qn++) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < CELLS; i++) {
+                        const __half hv = __float2half_rn(sv[SAVE ? qn : 0][i]);
+                        sts_u16(st_s + 2u * ((8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul), *reinterpret_cast<const uint16_t *>(&hv));
+                    }
+                    __syncwarp();
+                    if (lane < NC && col0 + lane < cnt)
+                        *reinterpret_cast<uint4 *>(p.save + (((size_t)t * N + row0 + col0 + lane) * 5 + qn) * XB_FEATURES + j * 32 + q * 8) =
+                            lds_v4(st_s + 2u * (lane * ST_PITCH));
+                }
+            }
             if (ew == 0 && lane == 0) DBG(sub, 12);
             if (p.one_release) {
                 // one release per sub-batch and step instead of one per warp (MEMBAR.GPU instances of one SM appear to
@@ -434,8 +452,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     }
 }
 
-template <bool BF16, int SUB, int NS, int EW, int GB = 2>
-int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
+template <bool BF16, int SUB, int NS, int EW, int GB = 2, bool SAVE = false>
+int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s, void *save = nullptr) {
     using C = Cfg<SUB, NS, EW, GB>;
     CUtensorMap tmY, tmG;
     if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
@@ -444,7 +462,7 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
     if (max_groups < 1)
         return xb_fail(h, XB_ERR_UNSUPPORTED, "the persistent LSTM needs %d co-resident CTAs, the device has %d SMs", TILES, h->num_sms);
     const int block_cap = max_groups * C::NB;
-    auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW, GB>;
+    auto fn = lstm_persistent_kernel<BF16, SUB, NS, EW, GB, SAVE>;
     static bool configured[64] = {};      // per device: function attributes live in the device's context
     if (!configured[h->device & 63]) {
         XB_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -462,6 +480,7 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
         p.one_release = 1;
         p.prefetch_y = 4;
         p.dbg = nullptr;
+        p.save = reinterpret_cast<uint16_t *>(save);
 #ifdef XB_EXPERIMENTS
         if (getenv("XB_LSTM_WARP_RELEASE")) p.one_release = 0;
         if (getenv("XB_LSTM_PREFETCH_Y")) p.prefetch_y = atoi(getenv("XB_LSTM_PREFETCH_Y"));
@@ -489,7 +508,8 @@ extern "C" int xb_debug_lstm_timeline(xb_handle *h, long long *out_host) {
 
 // Recurrent part of one LSTM layer.  h->gates must already hold the input projection (T*N, 3072) with the
 // columns of every 128-wide tile ordered [unit][i,f,g,o] (weight repack mode 3 in xb_api.cu).
-int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s) {
+// save != nullptr: the training forward, which also stores (T, N, 5, 768) fp16 = i, f, g, o, c for the backward pass
+int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s, void *save) {
     if (!h->lstm_counters) {
         void *q = nullptr;
         XB_CUDA(h, cudaMalloc(&q, MAX_CTRS * CTR_STRIDE * sizeof(int) + 8 * 8 * 16 * sizeof(long long)));
@@ -506,5 +526,6 @@ int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, i
     if (variant == 2)
         return launch_cfg<false, 6, 16, 4>(h, layer, y_tnc, T, N, reverse, s);
 #endif
+    if (save) return launch_cfg<false, 3, 32, 8, 2, true>(h, layer, y_tnc, T, N, reverse, s, save);
     return launch_cfg<false, 3, 32, 8>(h, layer, y_tnc, T, N, reverse, s);
 }

@@ -59,6 +59,14 @@ __global__ void stitch_kernel(const int8_t *__restrict__ rows, int T, const int3
     if (lane == 0) out_len[r] = min(pos, out_stride);
 }
 
+// posteriors(scores, Max) = one-hot at the arg-max edge of every (t, n): zero the row, set one element
+__global__ void onehot_edges_kernel(const int32_t *__restrict__ edges_nt, int T, int N, int S, float *__restrict__ post) {
+    const int t = blockIdx.x, n = blockIdx.y;
+    float *row = post + ((size_t)t * N + n) * S;
+    const int e = edges_nt[(size_t)n * T + t];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) row[i] = (i == e) ? 1.0f : 0.0f;
+}
+
 // ---- chunk gather ------------------------------------------------------------------------------------
 // util.chunk (bonito/util.py:152-166) for a whole read set on the device: chunk c of the batch is samples
 // [start, start + L) of read chunk_read[c]; start < 0 means a short read, left-padded with zeros (:160).
@@ -232,6 +240,12 @@ int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk
     return XB_OK;
 }
 
+int xb_onehot_edges(xb_handle *h, const int32_t *edges_nt, int T, int N, int S, float *post, cudaStream_t s) {
+    onehot_edges_kernel<<<dim3(T, N), 256, 0, s>>>(edges_nt, T, N, S, post);
+    XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
 int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
                           const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
                           int L, float *out, cudaStream_t s) {
@@ -254,7 +268,7 @@ int xb_ctc_loss_impl(xb_handle *h, const float *scores, int T, int N, const int3
     const int npos = Lmax - (h->state_len - 1);
     XB_REQUIRE(h, npos >= 1 && npos <= 1024, "Lmax=%d unsupported (1 <= Lmax-state_len+1 <= 1024)", Lmax);
     if (normalise)
-        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, s)) return rc;
+        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, 0, s)) return rc;
     const int NT = ((npos + 31) / 32) * 32;
     const int S = h->C * h->NZ;
     size_t smem = sizeof(float) * (2 * NT + 2 * S);

@@ -21,7 +21,7 @@ int xb_fail(xb_handle *h, int code, const char *fmt, ...) {
 }
 
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
-int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s);
+int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s, void *save = nullptr);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
 int xb_head_astationary_launch(xb_handle *h, const void *x, const void *w, int w_rows, const float *bias, int head_rows,
                                float *scores, int ldo, int M, int exp_out, cudaStream_t s);
@@ -37,6 +37,8 @@ int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk
                    const int32_t *read_len, int n_reads, int chunksize, int overlap, int stride, int reverse, int8_t *out,
                    int out_stride, int32_t *out_len, cudaStream_t s);
 
+void xb_train_free(xb_handle *h);
+int xb_onehot_edges(xb_handle *h, const int32_t *edges_nt, int T, int N, int S, float *post, cudaStream_t s);
 int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
                           const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
                           int L, float *out, cudaStream_t s);
@@ -81,6 +83,15 @@ __global__ void repack_kernel(const float *__restrict__ src, uint16_t *__restric
     } else if (mode == 4) {
         int j = r >> 7, q = (r >> 5) & 3, g = (r >> 3) & 3, ul = r & 7;
         v = src[(size_t)(g * XB_FEATURES + j * 32 + q * 8 + ul) * cols_src + c];
+    } else if (mode == 5 || mode == 6) {      // transposes for the training backward, stored as bf16: dst (cols_src.., rows_src..) = src^T
+        if (mode == 5) { if (r < cols_src && c < rows_src) v = src[(size_t)c * cols_src + r]; }
+        else {                                 // conv3 (768,16,19) -> (320, 768): row tap*16 + ch
+            int tap = r >> 4, ch = r & 15;
+            if (tap < XB_WINLEN) v = src[((size_t)c * XB_C2_CH + ch) * XB_WINLEN + tap];
+        }
+        __nv_bfloat16 bv = __float2bfloat16_rn(v);
+        dst[i] = *reinterpret_cast<uint16_t *>(&bv);
+        return;
     } else {
         int tap = c >> 4, ch = c & 15;
         if (tap < XB_WINLEN) v = src[((size_t)r * XB_C2_CH + ch) * XB_WINLEN + tap];
@@ -237,10 +248,12 @@ int xb_destroy(xb_handle *h) {
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto &l : h->lstm) {
-        if (l.w_ih) cudaFree(l.w_ih);
-        if (l.w_hh) cudaFree(l.w_hh);
-        if (l.bias) cudaFree(l.bias);
+        for (void *p : {l.w_ih, l.w_hh, (void *)l.bias, l.w_ihT, l.w_hhT})
+            if (p) cudaFree(p);
     }
+    if (h->head_wT) cudaFree(h->head_wT);
+    if (h->conv3_wT) cudaFree(h->conv3_wT);
+    xb_train_free(h);
     delete h;
     return XB_OK;
 }
@@ -286,6 +299,10 @@ int xb_load_conv_weights(xb_handle *h, const float *w1, const float *b1, const f
     XB_CUDA(h, cudaMemcpyAsync(h->conv2_w, w2, 320 * 4, cudaMemcpyDeviceToDevice, s));
     XB_CUDA(h, cudaMemcpyAsync(h->conv2_b, b2, 16 * 4, cudaMemcpyDeviceToDevice, s));
     if (int rc = repack(h, w3, h->conv3_w, F, XB_CONV3_K, F, XB_C2_CH * XB_WINLEN, 2, s)) return rc;
+    if (h->flags & XB_FLAG_TRAIN) {
+        if (!h->conv3_wT) { if (int rc = dev_alloc_bytes(h, &h->conv3_wT, (size_t)XB_CONV3_K * F * 2)) return rc; }
+        if (int rc = repack(h, w3, h->conv3_wT, XB_CONV3_K, F, F, XB_C2_CH * XB_WINLEN, 6, s)) return rc;
+    }
     XB_CUDA(h, cudaMemcpyAsync(h->conv3_b, b3, F * 4, cudaMemcpyDeviceToDevice, s));
     h->loaded |= 1;
     return XB_OK;
@@ -305,6 +322,13 @@ int xb_load_lstm_weights(xb_handle *h, int layer, const float *w_ih, const float
 #endif
     if (int rc = repack(h, w_ih, h->lstm[layer].w_ih, XB_GATES, F, XB_GATES, F, ih_mode, s)) return rc;
     if (int rc = repack(h, w_hh, h->lstm[layer].w_hh, XB_GATES, F, XB_GATES, F, ih_mode == 3 ? 4 : 1, s)) return rc;
+    if (h->flags & XB_FLAG_TRAIN) {
+        xb_lstm_weights &lw = h->lstm[layer];
+        if (!lw.w_ihT) { if (int rc = dev_alloc_bytes(h, &lw.w_ihT, (size_t)XB_GATES * F * 2)) return rc; }
+        if (!lw.w_hhT) { if (int rc = dev_alloc_bytes(h, &lw.w_hhT, (size_t)XB_GATES * F * 2)) return rc; }
+        if (int rc = repack(h, w_ih, lw.w_ihT, F, XB_GATES, XB_GATES, F, 5, s)) return rc;
+        if (int rc = repack(h, w_hh, lw.w_hhT, F, XB_GATES, XB_GATES, F, 5, s)) return rc;
+    }
     lstm_bias_kernel<<<(XB_GATES + 255) / 256, 256, 0, s>>>(b_ih, b_hh, h->lstm[layer].bias, ih_mode);
     XB_LAUNCH_CHECK(h);
     h->loaded |= 2 << layer;
@@ -317,6 +341,10 @@ int xb_load_head_weights(xb_handle *h, const float *w, const float *b, float sca
     XB_REQUIRE(h, w != nullptr, "NULL head weight");
     const int F = XB_FEATURES;
     if (int rc = repack(h, w, h->head_w, h->head_rows_padded, F, h->head_rows, F, 0, s)) return rc;
+    if (h->flags & XB_FLAG_TRAIN) {
+        if (!h->head_wT) { if (int rc = dev_alloc_bytes(h, &h->head_wT, (size_t)h->head_rows_padded * F * 2)) return rc; }
+        if (int rc = repack(h, w, h->head_wT, F, h->head_rows_padded, h->head_rows, F, 5, s)) return rc;
+    }
     XB_CUDA(h, cudaMemsetAsync(h->head_b, 0, (size_t)h->head_rows_padded * 4, s));
     if (b) XB_CUDA(h, cudaMemcpyAsync(h->head_b, b, (size_t)h->head_rows * 4, cudaMemcpyDeviceToDevice, s));
     h->scale = scale;
@@ -494,21 +522,49 @@ int xb_basecall_chunks(xb_handle *h, const void *signal, int sig_dtype, int N, i
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream)
 
 int xb_crf_logz(xb_handle *h, const float *scores, int T, int N, float *logz, void *stream) {
-    XB_CRF_PROLOGUE();
-    XB_REQUIRE(h, logz != nullptr, "logz is NULL");
-    return xb_decode_alpha(h, scores, T, N, nullptr, logz, s);
+    return xb_crf_logz_s(h, scores, T, N, XB_SEMIRING_LOG, logz, stream);
 }
 
 int xb_crf_forward_scores(xb_handle *h, const float *scores, int T, int N, float *alpha, void *stream) {
-    XB_CRF_PROLOGUE();
-    XB_REQUIRE(h, alpha != nullptr, "alpha is NULL");
-    return xb_decode_alpha(h, scores, T, N, alpha, nullptr, s);
+    return xb_crf_forward_scores_s(h, scores, T, N, XB_SEMIRING_LOG, alpha, stream);
 }
 
 int xb_crf_backward_scores(xb_handle *h, const float *scores, int T, int N, float *beta, void *stream) {
+    return xb_crf_backward_scores_s(h, scores, T, N, XB_SEMIRING_LOG, beta, stream);
+}
+
+#define XB_SEMIRING_CHECK() XB_REQUIRE(h, semiring == XB_SEMIRING_LOG || semiring == XB_SEMIRING_MAX, "unknown semiring %d", semiring)
+
+int xb_crf_logz_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *logz, void *stream) {
     XB_CRF_PROLOGUE();
+    XB_SEMIRING_CHECK();
+    XB_REQUIRE(h, logz != nullptr, "logz is NULL");
+    return xb_decode_alpha(h, scores, T, N, nullptr, logz, semiring == XB_SEMIRING_MAX, s);
+}
+
+int xb_crf_forward_scores_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *alpha, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_SEMIRING_CHECK();
+    XB_REQUIRE(h, alpha != nullptr, "alpha is NULL");
+    return xb_decode_alpha(h, scores, T, N, alpha, nullptr, semiring == XB_SEMIRING_MAX, s);
+}
+
+int xb_crf_backward_scores_s(xb_handle *h, const float *scores, int T, int N, int semiring, float *beta, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_SEMIRING_CHECK();
     XB_REQUIRE(h, beta != nullptr, "beta is NULL");
-    return xb_decode_backward(h, scores, T, N, nullptr, beta, 2, s);
+    return xb_decode_backward(h, scores, T, N, beta, beta, semiring == XB_SEMIRING_MAX ? 1 : 2, s);
+}
+
+// posteriors(scores, Max): one-hot at the arg-max edge of the max-marginals of every step (first index on ties).
+// edges_nt (N, T) int32 receives the flat edge index c*NZ + k; post (T, N, C*NZ), if given, the one-hot tensor.
+int xb_crf_posteriors_max(xb_handle *h, const float *scores, int T, int N, int32_t *edges_nt, float *post, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, edges_nt != nullptr, "edges is NULL");
+    if (int rc = xb_decode_backward(h, scores, T, N, h->bmax, nullptr, 1, s)) return rc;
+    if (int rc = xb_decode_viterbi_fwd(h, scores, h->bmax, T, N, nullptr, nullptr, nullptr, nullptr, edges_nt, s)) return rc;
+    if (post) return xb_onehot_edges(h, edges_nt, T, N, h->C * h->NZ, post, s);
+    return XB_OK;
 }
 
 int xb_crf_posteriors(xb_handle *h, const float *scores, int T, int N, float *post, void *stream) {
@@ -521,7 +577,7 @@ int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labe
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, labels_nt != nullptr, "labels is NULL");
     if (int rc = xb_decode_backward(h, scores, T, N, h->bmax, nullptr, 1, s)) return rc;
-    return xb_decode_viterbi_fwd(h, scores, h->bmax, T, N, labels_nt, nullptr, nullptr, nullptr, s);
+    return xb_decode_viterbi_fwd(h, scores, h->bmax, T, N, labels_nt, nullptr, nullptr, nullptr, nullptr, s);
 }
 
 int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring, int32_t *lens,
@@ -552,7 +608,7 @@ int xb_ctc_crf_loss_bwd(xb_handle *h, const float *scores, int T, int N, const i
     XB_REQUIRE(h, targets && lengths && grad_loss && alpha_ws && grad_scores, "NULL buffer");
     if (normalise) {       // logZ (for the shift) and the posteriors of the full lattice, straight into grad_scores
         if (int rc = xb_decode_lin(h, scores, 0, T, N, nullptr, nullptr, nullptr, nullptr, grad_scores, s)) return rc;
-        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, s)) return rc;
+        if (int rc = xb_decode_alpha(h, scores, T, N, nullptr, h->logz, 0, s)) return rc;
     }
     return xb_ctc_loss_bwd_impl(h, scores, T, N, targets, Lmax, lengths, normalise, grad_loss, alpha_ws, grad_scores, s);
 }

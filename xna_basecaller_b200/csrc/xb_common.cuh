@@ -24,6 +24,8 @@ struct xb_lstm_weights {
     void *w_ih = nullptr;        // (3072, 768) 16-bit, rows gate-interleaved (see xb_api.cu)
     void *w_hh = nullptr;        // (3072, 768) 16-bit, same row order
     float *bias = nullptr;       // (3072) fp32 = b_ih + b_hh, same row order
+    void *w_ihT = nullptr;       // XB_FLAG_TRAIN: (768, 3072) bf16 = W_ih^T, reference gate-row order (backward GEMM operand)
+    void *w_hhT = nullptr;       // XB_FLAG_TRAIN: (768, 3072) bf16 = W_hh^T
 };
 
 enum { XB_ST_CONV12 = 0, XB_ST_CONV3, XB_ST_INPROJ, XB_ST_LSTM_REC, XB_ST_HEAD, XB_ST_CRF_ALPHA, XB_ST_CRF_BACKWARD,
@@ -85,6 +87,11 @@ struct xb_handle {
     float *logz = nullptr;       // (max_N)
     float *ctc_ws = nullptr;
     int *lstm_counters = nullptr; // per-group step counters of the persistent LSTM kernel
+
+    // training (XB_FLAG_TRAIN; workspace allocated by the first xb_encoder_fwd_train, see train_bwd.cu)
+    void *head_wT = nullptr;     // (768, head_rows_padded) bf16 = W_head^T
+    void *conv3_wT = nullptr;    // (320, 768) bf16 = W_3^T in im2col column order
+    struct xb_train_ws *train = nullptr;
 
     // driver entry point for TMA descriptors (resolved at run time: no link-time libcuda dependency)
     void *encode_tiled = nullptr;
@@ -161,10 +168,10 @@ template <> struct xb16<true> {
 };
 
 // ---- entry points implemented in the other translation units ------------------------------------
-int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, cudaStream_t s);
+int xb_decode_alpha(xb_handle *h, const float *scores, int T, int N, float *alpha, float *logz, int use_max, cudaStream_t s);
 int xb_decode_backward(xb_handle *h, const float *scores, int T, int N, float *bmax, float *beta, int mode, cudaStream_t s);
 int xb_decode_lin(xb_handle *h, const float *scores, int lin_input, int T, int N, int8_t *labels, int8_t *seq, int8_t *qs,
                   int32_t *lens, float *post, cudaStream_t s);
 int xb_score_exp_launch(xb_handle *h, const float *in, float *out, size_t n, cudaStream_t s);
 int xb_decode_viterbi_fwd(xb_handle *h, const float *lp, const float *bmax, int T, int N, int8_t *labels,
-                          int8_t *seq, int8_t *qstring, int32_t *lens, cudaStream_t s);
+                          int8_t *seq, int8_t *qstring, int32_t *lens, int32_t *edges, cudaStream_t s);
