@@ -181,6 +181,15 @@ int xb_encoder_fwd_train(xb_handle *h, const void *signal, int sig_dtype, int N,
 int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float *scores, const float *dscores,
                    float *const *grads, int n_tensors, void *stream);
 
+/* The optimiser half of Trainer.train_one_step (training.py:112-115): torch.nn.utils.clip_grad_norm_(max_norm) followed by
+ * one torch.optim.AdamW step (training.py:183-184; decoupled weight decay, bias-corrected moments) over n_tensors fp32
+ * tensors given as host arrays of device pointers.  max_norm <= 0 disables clipping; step >= 1 counts this update;
+ * grad_norm (device, 1 float) receives the total gradient norm before clipping; scratch is device memory of
+ * 4 * (sum_i ceil(numel[i] / 65536) + 1) bytes.  Needs no handle. */
+int xb_adamw_step(float *const *params, float *const *grads, float *const *exp_avg, float *const *exp_avg_sq,
+                  const int64_t *numel, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float max_norm, int64_t step, float *grad_norm, float *scratch, void *stream);
+
 /* util.stitch over left-packed chunks (util.py:169-188; crf/basecall.py:15-24): for each read r,
  * concatenates slices of its chunks' packed rows.  chunk_first[r], chunk_count[r], read_len[r]
  * (samples) describe the reads; rows are (n_chunks_total, T) int8; out is (n_reads, out_stride) int8,

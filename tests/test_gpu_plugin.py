@@ -236,7 +236,7 @@ def test_bf16_end_to_end_identical_read_rate(golden):
         def __init__(self, rid, sig):
             self.read_id, self.signal = rid, sig
 
-    for dtype, max_rate in ((torch.float16, 0.05), (torch.bfloat16, 0.15)):
+    for dtype, max_rate in ((torch.float16, 0.02), (torch.bfloat16, 0.03)):      # measured: 4/4 identical reads in both modes
         mm = m.to(dtype).eval().to('cuda')
         got = {r.read_id: res['sequence'] for r, res in
                util.load_symbol(cfg, 'basecall')(mm, iter([Read(k, s) for k, s in reads]), chunksize=1000, overlap=100, batchsize=4)}

@@ -62,3 +62,71 @@ def test_encoder_backward_matches_autograd(n_base, N, L):
     for layer in range(4, 9):
         assert torch.equal(got['encoder.%d.rnn.bias_hh_l0' % layer], got['encoder.%d.rnn.bias_ih_l0' % layer])
     h.close()
+
+
+def test_adamw_step_matches_torch():
+    """xb_adamw_step (clip_grad_norm_(2.0) + AdamW) against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW over five
+    steps on tensors of the model's shapes (one larger than a 65536-element block, one tiny)."""
+    from xna_basecaller_b200.training import AdamW
+    g = torch.Generator(device='cuda').manual_seed(3)
+    shapes = [(3072, 768), (625, 768), (3072,), (4, 1, 5), (16,)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device='cuda', generator=g) * 0.1) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    kw = dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    opt, opt_ref = AdamW(ours, **kw), torch.optim.AdamW(ref, **kw)
+    for step in range(5):
+        scale = 10.0 if step % 2 == 0 else 1e-3               # one step clipped, one not
+        for p, q in zip(ours, ref):
+            p.grad = torch.randn(p.shape, device='cuda', generator=g) * scale
+            q.grad = p.grad.clone()
+        norm = opt.step(max_norm=2.0).item()
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref, max_norm=2.0).item()
+        opt_ref.step()
+        assert abs(norm - norm_ref) <= 1e-5 * norm_ref
+        for p, q in zip(ours, ref):
+            assert (p - q).abs().max().item() <= 2e-6
+    assert opt.state[ours[0]]['step'] == 5
+
+
+def test_trainer_train_one_step_through_the_plugin():
+    """Trainer.train_one_step (training.py:91-117) on the plugin Model: loss.backward() reaches every parameter through
+    xb_ctc_crf_loss_bwd + xb_encoder_bwd, gradients equal the direct C-ABI calls, and a few clipped AdamW steps on one
+    batch lower the loss."""
+    from make_golden import synthetic_targets
+    from xna_basecaller_b200 import util
+    from xna_basecaller_b200.training import Trainer
+    cfg = {'global_norm': {'state_len': 3}, 'input': {'features': 1}, 'labels': {'labels': ALPHABETS[5]},
+           'model': {'package': 'xna_basecaller_b200.crf'},
+           'encoder': {'stride': 5, 'activation': 'swish', 'features': 768, 'winlen': 19, 'scale': 5.0,
+                       'rnn_type': 'lstm', 'blank_score': 2.0}}
+    model = util.load_symbol(cfg, 'Model')(cfg)
+    sd = bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE)
+    model.load_state_dict(sd)
+    N, L = 8, 600
+    x = synthetic_signal(51, N, L)
+    tg, tl = synthetic_targets(7, N, 5, 40, 60)
+    trainer = Trainer(model, 'cuda')
+    trainer.init_optimizer(1e-3)
+    model.train()
+    # gradients of one forward / backward through autograd == the oracle's autograd on the same loss
+    scores = model(x.cuda())
+    loss = model.seqdist.ctc_loss(scores.float(), tg.cuda(), tl.cuda())
+    loss.backward()
+    params = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ref_loss = bo.CRF(3, ALPHABETS[5]).ctc_loss(bo.encoder_forward(params, x, 5), tg, tl)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    named = dict(model.named_parameters())
+    for k, q in params.items():
+        if k.endswith('bias_hh_l0'):
+            continue                                   # frozen at zero in the reference (nn.py:209-213): no gradient
+        a, b = named[k].grad.double().cpu().flatten(), q.grad.double().flatten()
+        rel = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        assert rel <= 5e-2, (k, rel)
+    first = None
+    for step in range(6):
+        losses, grad_norm = trainer.train_one_step((x, tg, tl))
+        assert np.isfinite(losses['loss']) and np.isfinite(grad_norm) and grad_norm > 0
+        first = losses['loss'] if first is None else first
+    assert losses['loss'] < first
+    print('loss %.4f -> %.4f in 6 steps, last grad norm %.3f' % (first, losses['loss'], grad_norm))

@@ -26,7 +26,7 @@ SYMBOLS = (
     'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_compute_scores_submit', 'xb_compute_scores_wait', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times', 'xb_crf_head_fwd_exp', 'xb_crf_decode_exp', 'xb_basecall_chunks',
     'xb_crf_logz_s', 'xb_crf_forward_scores_s', 'xb_crf_backward_scores_s', 'xb_crf_posteriors_max',
-    'xb_encoder_fwd_train', 'xb_encoder_bwd',
+    'xb_encoder_fwd_train', 'xb_encoder_bwd', 'xb_adamw_step',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
           'crf_backward', 'crf_viterbi')
@@ -65,6 +65,8 @@ def load():
     lib.xb_crf_posteriors.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.xb_encoder_fwd_train.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_encoder_bwd.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(vp), ci, vp]
+    lib.xb_adamw_step.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                  ctypes.POINTER(ctypes.c_int64), ci, cf, cf, cf, cf, cf, cf, ctypes.c_int64, vp, vp, vp]
     lib.xb_crf_logz_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_crf_forward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_crf_backward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]

@@ -40,7 +40,8 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
     T = L // model.stride
     if reverse or batch.device.type != 'cpu':
         # reverse complement permutes the score tensor between encoder and decode: two device calls
-        scores = model(batch.to(device))
+        with torch.no_grad():
+            scores = model(batch.to(device))
         if reverse:
             scores = model.seqdist.reverse_complement(scores)
         seq, qs, lens = model.seqdist.decode_packed(scores)

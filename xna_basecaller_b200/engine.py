@@ -23,8 +23,8 @@ class Engine:
         self.stamps = {}
 
     # ------------------------------------------------------------------ handle life cycle
-    def get(self, device, N, T, bf16=False, encoder=True):
-        """Handle on `device` with capacity >= (N, T)."""
+    def get(self, device, N, T, bf16=False, encoder=True, train=False):
+        """Handle on `device` with capacity >= (N, T); train=True: one that keeps what the encoder backward needs."""
         device = torch.device(device)
         if device.type != 'cuda':
             raise RuntimeError('xna_basecaller_b200 computes on a CUDA device (sm_100a) only; got tensors on %s. '
@@ -33,15 +33,16 @@ class Engine:
             device = torch.device('cuda', torch.cuda.current_device())
         h = self.handle
         if (h is None or h.device != device or h.bf16 != bf16 or h.max_N < N or h.max_T < T
-                or (encoder and not h.has_encoder)):
+                or (encoder and not h.has_encoder) or (train and not h.train)):
             max_N = max(N, h.max_N if h is not None and h.device == device else 0)
             max_T = max(T, h.max_T if h is not None and h.device == device else 0)
             need_enc = encoder or (h is not None and h.has_encoder)
+            train = train or (h is not None and h.train)
             # The outgoing handle is NOT destroyed here: an in-flight pipelined batch (crf/basecall.py::_submit_scores), a
             # _CTCLoss context between forward and backward or a ReadSetBasecaller may still hold it.  Dropping our
             # reference lets Handle.__del__ run xb_destroy when its last user lets go.
             self.handle = _lib.Handle(self.alphabet, self.state_len, max_N=max_N, max_T=max_T, device=device,
-                                      bf16=bf16, encoder=need_enc)
+                                      bf16=bf16, encoder=need_enc, train=train)
             self.handle.has_encoder = need_enc
             self.stamps = {}
         return self.handle

@@ -117,10 +117,37 @@ class Serial(torch.nn.Sequential):
             return None
         return c1, c2, c3
 
+    def _training_layout(self):
+        """(stem, five LSTMs, head) when this is the whole sup@v3.3 encoder -- the layout the fused training step
+        (xb_encoder_fwd_train / xb_encoder_bwd) is built for -- else None."""
+        stem = self._stem()
+        mods = [m for m in list(self)[4:] if not isinstance(m, torch.nn.Dropout)] if stem is not None else []
+        if len(mods) != 6 or not all(isinstance(m, LSTM) for m in mods[:5]) or not isinstance(mods[5], LinearCRFEncoder):
+            return None
+        if [m.reverse for m in mods[:5]] != [True, False, True, False, True]:
+            return None
+        head = mods[5]
+        if head.extra_linear or not head.expand_blanks or head.blank_score is None or head.linear.bias is None:
+            return None
+        return stem, mods[:5], head
+
     def forward(self, x):
         mods = list(self)
         stem = self._stem()
         start = 0
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the training step (bonito/training.py:91-117, after model.train()): one fused forward that keeps the backward's
+            # inputs, and an autograd node whose backward is xb_encoder_bwd.  In eval mode (load_model, the basecaller) the
+            # layers run the inference kernels and no graph is recorded.
+            layout = self._training_layout()
+            if layout is None or x.dim() != 3 or x.shape[1] != 1:
+                raise RuntimeError('gradients are implemented for the whole sup@v3.3 encoder (conv stem, five LSTMs in the '
+                                   'reference directions, LinearCRFEncoder with expand_blanks); run other layouts under '
+                                   'torch.no_grad()')
+            for m in mods:
+                if isinstance(m, torch.nn.Dropout) and m.training and m.p > 0:
+                    raise RuntimeError('dropout is not part of the B200 path')
+            return _encoder_train_forward(self, layout, x)
         if stem is not None and x.dim() == 3 and x.shape[1] == 1:
             x = _conv_stem_forward(self, stem, x)
             start = 4
@@ -144,6 +171,35 @@ class Serial(torch.nn.Sequential):
 
     def to_dict(self, include_weights=False):
         return {'sublayers': [to_dict(layer, include_weights) for layer in self._modules.values()]}
+
+
+class _EncoderTrain(torch.autograd.Function):
+    """scores = encoder(x) with a backward that fills the gradients of the 28 parameter tensors (xb_encoder_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, handle, *params):
+        ctx.handle, ctx.dtypes = handle, [p.dtype for p in params]
+        return handle.encoder_train(x)
+
+    @staticmethod
+    def backward(ctx, dscores):
+        grads = ctx.handle.encoder_backward(dscores)
+        return (None, None) + tuple(grads[k].to(dt) for k, dt in zip(ctx.handle.WEIGHT_KEYS, ctx.dtypes))
+
+
+def _encoder_train_forward(owner, layout, x):
+    stem, lstms, head = layout
+    eng = _engine_of(owner)
+    N, _, L = x.shape
+    if L % 5:
+        raise ValueError('chunk length %d is not a multiple of the stride 5' % L)
+    h = eng.get(x.device, N, L // 5, bf16=_is_bf16(owner), train=True)
+    owner.sync_weights(h)
+    params = [t for c in stem for t in (c.conv.weight, c.conv.bias)]
+    for m in lstms:
+        params += [m.rnn.weight_ih_l0, m.rnn.weight_hh_l0, m.rnn.bias_ih_l0, m.rnn.bias_hh_l0]
+    params += [head.linear.weight, head.linear.bias]
+    return _EncoderTrain.apply(x, h, *params)
 
 
 def _sync_stem(eng, stem):
