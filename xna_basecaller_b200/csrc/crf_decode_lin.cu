@@ -93,11 +93,29 @@ template <int NB, int SL> struct Ring {
     }
 };
 
+// Thread roles of the three sweeps: W = NT / 32 COMPUTE warps (one thread per state; they meet at named barrier 1 once per
+// step to exchange the state vector) and one SERVICE warp that runs ahead on its own: it waits for a ring slot to be
+// released (mbarrier `empty`, one arrival per compute warp), issues the bulk copies of the row D-1 steps ahead, and -- in
+// the Viterbi sweep -- reduces the per-warp arg-max candidates of a step to its label.  Keeping the copy issue and that
+// serial reduction out of the compute warps took a third off the per-step latency (the whole CTA used to wait at the
+// barrier for the one warp that had done them).
+template <int NB, int SL> struct Roles {
+    using L = Lat<NB, SL>;
+    static constexpr int NT = L::NT, W = L::W, NTT = NT + 32;
+};
+__device__ __forceinline__ void compute_bar(int nt) { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); }
+// The service warp runs D-1 steps ahead and spends most of its life waiting for a slot to be released: it must not burn
+// issue slots doing so (a bare try_wait loop re-issues every few dozen cycles; ncu showed it executing a third of the
+// CTA's instructions), and nothing is lost if it notices a free slot a few hundred nanoseconds late.
+__device__ __forceinline__ void service_wait(uint64_t *bar, uint32_t parity) {
+    while (!xbptx::mbar_try_wait(bar, parity)) __nanosleep(256);
+}
+
 // --------------------------------------------------------------------------------------------------
 // Sweep 1, forward: a_hat_0 = 1;  u_{t+1}[c] = fma-chain_k E_t[c,k] * a_hat_t[src(c,k)];  a_hat = u * scale(max u).
 // The scale of a vector is known one barrier after the vector, so a_hat_t is applied (and stored) at step t.
 template <int NB, int SL, bool LIN>
-__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+__global__ void __launch_bounds__(Lat<NB, SL>::NT + 32)
 crf_lin_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__restrict__ alpha_out) {
     using L = Lat<NB, SL>;
     using R = Ring<NB, SL>;
@@ -106,23 +124,35 @@ crf_lin_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__re
     float *ring = smem;                      // D * ROWF
     float *u = ring + D * R::ROWF;           // 2 * NT
     float *red = u + 2 * NT;                 // 2 * W
-    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * W + (2 * W & 1));      // D barriers, 8-byte aligned
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(red + 2 * W) + 7) & ~uintptr_t(7));   // D + D barriers
+    uint64_t *empty = full + D;
     const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
-    const bool act = c < C, producer = c == NT - 1;
     const size_t total_rows = (size_t)T * N;
-    if (producer) {
-        for (int j = 0; j < D; j++) xbptx::mbar_init(&full[j], 1);
+    if (c == NT) {
+        for (int j = 0; j < D; j++) { xbptx::mbar_init(&full[j], 1); xbptx::mbar_init(&empty[j], W); }
         xbptx::fence_barrier_init();
     }
-    u[c] = act ? 1.0f : 0.0f;
-    if (lane == 0) red[w] = 1.0f;
+    if (c < NT) {
+        u[c] = c < C ? 1.0f : 0.0f;
+        if (lane == 0) red[w] = 1.0f;
+    }
     __syncthreads();
-    if (producer)
-        for (int j = 0; j < D - 1 && j < T; j++) {
-            const size_t rid = (size_t)j * N + n;
-            xbptx::mbar_expect_tx(&full[j], R::row_tx(rid, total_rows));
-            R::fetch_row(ring + j * R::ROWF, scores, rid, total_rows, &full[j]);
+    if (w == W) {                            // ---------------- service warp
+        if (lane == 0) {
+            auto fetch = [&](int r) {
+                const size_t rid = (size_t)r * N + n;
+                xbptx::mbar_expect_tx(&full[r % D], R::row_tx(rid, total_rows));
+                R::fetch_row(ring + (r % D) * R::ROWF, scores, rid, total_rows, &full[r % D]);
+            };
+            for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
+            for (int t = 0; t + D - 1 < T; t++) {
+                if (t > 0) service_wait(&empty[(t - 1) % D], ((t - 1) / D) & 1);
+                fetch(t + D - 1);
+            }
         }
+        return;
+    }
+    const bool act = c < C;
     int src[NZ];
     src[0] = act ? c : 0;
 #pragma unroll
@@ -133,30 +163,29 @@ crf_lin_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__re
     for (int t = 0; t < T; t++) {
         const int slot = t % D;
         xbptx::mbar_wait(&full[slot], (t / D) & 1);
-        __syncthreads();
-        if (producer && t + D - 1 < T) {
-            const int r = t + D - 1;
-            const size_t rid = (size_t)r * N + n;
-            xbptx::mbar_expect_tx(&full[r % D], R::row_tx(rid, total_rows));
-            R::fetch_row(ring + (r % D) * R::ROWF, scores, rid, total_rows, &full[r % D]);
-        }
+        compute_bar(NT);
         const float sc = xb_pow2_scale(red_max<W>(red + (t & 1) * W));
         const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n) + c * NZ;
         const float *uc = u + (t & 1) * NT;
         float acc = 0.0f;
         if (act) {
-            *aout = XB_MUL(uprev, sc);
-            acc = XB_MUL(edge_E<LIN>(M[0]), XB_MUL(uc[src[0]], sc));
+            float e[NZ];
 #pragma unroll
-            for (int k = 1; k < NZ; k++) acc = XB_FMA(edge_E<LIN>(M[k]), XB_MUL(uc[src[k]], sc), acc);
+            for (int k = 0; k < NZ; k++) e[k] = edge_E<LIN>(M[k]);
+            *aout = XB_MUL(uprev, sc);
+            acc = XB_MUL(e[0], XB_MUL(uc[src[0]], sc));
+#pragma unroll
+            for (int k = 1; k < NZ; k++) acc = XB_FMA(e[k], XB_MUL(uc[src[k]], sc), acc);
             u[((t + 1) & 1) * NT + c] = acc;
             uprev = acc;
         }
+        __syncwarp();
+        if (lane == 0) xbptx::mbar_arrive(&empty[slot]);
         aout += arow;
         const float wm = warp_max_pos(acc);
         if (lane == 0) red[((t + 1) & 1) * W + w] = wm;
     }
-    __syncthreads();
+    compute_bar(NT);
     if (act) *aout = XB_MUL(uprev, xb_pow2_scale(red_max<W>(red + (T & 1) * W)));
 }
 
@@ -168,7 +197,7 @@ crf_lin_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__re
 //     um_{t+1}[s] = max_e (x_e(t+1) / tot_{t+1} + 1e-8) * bm_hat_{t+2}[dst_e]
 // with the x_e of the previous iteration held in registers.  tot_t is stored in slot NT of the b_hat_{t+1} vector.
 template <int NB, int SL, bool LIN>
-__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+__global__ void __launch_bounds__(Lat<NB, SL>::NT + 32)
 crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restrict__ alpha, int T, int N,
                         float *__restrict__ beta_out, float *__restrict__ bmax_out) {
     using L = Lat<NB, SL>;
@@ -182,30 +211,41 @@ crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restric
     float *redb = um + 2 * NT;               // 2 * W
     float *redm = redb + 2 * W;              // 2 * W
     float *part = redm + 2 * W;              // 2 * W
-    uint64_t *full = reinterpret_cast<uint64_t *>(part + 2 * W);       // D barriers (6 W floats: 8-byte aligned)
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(part + 2 * W) + 7) & ~uintptr_t(7));   // D + D barriers
+    uint64_t *empty = full + D;
     const int n = blockIdx.x, s = threadIdx.x, lane = s & 31, w = s >> 5;
-    const bool act = s < C, producer = s == NT - 1;
     const size_t total_rows = (size_t)T * N;
     const size_t vrow = (size_t)N * R::VP;
-    const float *abase = alpha + (size_t)n * R::VP;
-    auto fetch = [&](int r) {                // iteration r: score row and a_hat of step T-1-r
-        const int t = T - 1 - r, slot = r % D;
-        const size_t rid = (size_t)t * N + n;
-        xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + R::VECB);
-        R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
-        bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
-    };
-    if (producer) {
-        for (int j = 0; j < D; j++) xbptx::mbar_init(&full[j], 1);
+    if (s == NT) {
+        for (int j = 0; j < D; j++) { xbptx::mbar_init(&full[j], 1); xbptx::mbar_init(&empty[j], W); }
         xbptx::fence_barrier_init();
     }
     // buffers are read at parity q = i & 1 and written at q ^ 1; the Max recursion starts at iteration 1 (parity 1)
-    ub[s] = act ? 1.0f : 0.0f;
-    um[NT + s] = act ? 1.0f : 0.0f;
-    if (lane == 0) { redb[w] = 1.0f; redm[W + w] = 1.0f; }
+    if (s < NT) {
+        ub[s] = s < C ? 1.0f : 0.0f;
+        um[NT + s] = s < C ? 1.0f : 0.0f;
+        if (lane == 0) { redb[w] = 1.0f; redm[W + w] = 1.0f; }
+    }
     __syncthreads();
-    if (producer)
-        for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
+    if (w == W) {                            // ---------------- service warp
+        if (lane == 0) {
+            const float *abase = alpha + (size_t)n * R::VP;
+            auto fetch = [&](int r) {        // iteration r: score row and a_hat of step T-1-r
+                const int t = T - 1 - r, slot = r % D;
+                const size_t rid = (size_t)t * N + n;
+                xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + R::VECB);
+                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
+                bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
+            };
+            for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
+            for (int i = 0; i + D - 1 < T; i++) {
+                if (i > 0) service_wait(&empty[(i - 1) % D], ((i - 1) / D) & 1);
+                fetch(i + D - 1);
+            }
+        }
+        return;
+    }
+    const bool act = s < C;
     const int kk = act ? 1 + s / L::NP : 1, cb = act ? (s % L::NP) * NB : 0;
     int eidx[NZ], dst[NZ];               // edge index into the row / destination state, e = 0 stay, 1 + j moves
     eidx[0] = (act ? s : 0) * NZ; dst[0] = act ? s : 0;
@@ -221,9 +261,19 @@ crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restric
     for (int i = 0; i <= T; i++) {
         const int t = T - 1 - i, q = i & 1, slot = i % D;
         if (i < T) xbptx::mbar_wait(&full[slot], (i / D) & 1);
-        __syncthreads();
-        if (producer && i + D - 1 < T) fetch(i + D - 1);
+        compute_bar(NT);
         const float sb = xb_pow2_scale(red_max<W>(redb + q * W));
+        float ev[NZ], bv[NZ], a = 0.0f;
+        if (i < T && act) {                  // everything this step needs from the ring slot, then release it
+            const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n);
+#pragma unroll
+            for (int e = 0; e < NZ; e++) ev[e] = edge_E<LIN>(M[eidx[e]]);
+            a = ringA[slot * R::VP + s];
+        }
+        if (i < T) {
+            __syncwarp();
+            if (lane == 0) xbptx::mbar_arrive(&empty[slot]);
+        }
         if (act) *bout = XB_MUL(ubprev, sb);
         if (i >= 1) {                        // Max step t+1 with the x of the previous iteration
             float tot = part[q * W];
@@ -250,14 +300,14 @@ crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restric
         }
         bout -= vrow;
         if (i < T) {                         // Log step t
-            const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n);
             const float *bc = ub + q * NT;
             float su = 0.0f, sx = 0.0f;
             if (act) {
-                const float a = ringA[slot * R::VP + s];
+#pragma unroll
+                for (int e = 0; e < NZ; e++) bv[e] = XB_MUL(bc[dst[e]], sb);
 #pragma unroll
                 for (int e = 0; e < NZ; e++) {
-                    const float we = XB_MUL(edge_E<LIN>(M[eidx[e]]), XB_MUL(bc[dst[e]], sb));
+                    const float we = XB_MUL(ev[e], bv[e]);
                     x[e] = XB_MUL(a, we);
                     su = (e == 0) ? we : XB_ADD(su, we);
                     sx = (e == 0) ? x[e] : XB_ADD(sx, x[e]);
@@ -278,14 +328,14 @@ crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restric
 //     v_k = P_k * am_hat_t[src_k];  um_{t+1}[c] = max_k v_k;  candidate v_k * bm_hat_{t+1}[c]
 // arg-max over the flat edge index (first index on ties) -> label = edge % NZ -> letters -> left-packed row.
 template <int NB, int SL, bool LIN, bool POST>
-__global__ void __launch_bounds__(Lat<NB, SL>::NT)
+__global__ void __launch_bounds__(Lat<NB, SL>::NT + 32)
 crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict__ alpha, const float *__restrict__ beta,
                        const float *__restrict__ bmax, int T, int N,
                        int8_t *__restrict__ labels_out, int8_t *__restrict__ seq_out, int8_t *__restrict__ qs_out,
                        int32_t *__restrict__ lens_out, float *__restrict__ post_out, Alphabet abc) {
     using L = Lat<NB, SL>;
     using R = Ring<NB, SL>;
-    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D;
+    constexpr int C = L::C, NZ = L::NZ, S = L::S, NT = L::NT, W = L::W, D = L::D, NTT = NT + 32;
     extern __shared__ __align__(128) float smem[];
     float *ring = smem;                      // D * ROWF
     float *ringA = ring + D * R::ROWF;       // D * VP: a_hat_t (whole vector: sources)
@@ -293,80 +343,98 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
     float *ringM = ringB + D * R::VP;        // D * VP: bm_hat_{t+1}
     float *am = ringM + D * R::VP;           // 2 * NT
     float *redm = am + 2 * NT;               // 2 * W
-    float *bval = redm + 2 * W;              // 2 * W
-    int *bidx = reinterpret_cast<int *>(bval + 2 * W);      // 2 * W
-    uint64_t *full = reinterpret_cast<uint64_t *>(bidx + 2 * W);       // D barriers
-    int *scan = reinterpret_cast<int *>(full + D);          // NT + 1
-    int8_t *lab = reinterpret_cast<int8_t *>(scan + NT + 1);   // T
+    float *bval = redm + 2 * W;              // D * W: per-warp arg-max candidates of the last D steps
+    int *bidx = reinterpret_cast<int *>(bval + D * W);      // D * W
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bidx + D * W) + 7) & ~uintptr_t(7));   // 3 * D barriers
+    uint64_t *empty = full + D, *cand = empty + D;
+    int *scan = reinterpret_cast<int *>(cand + D);          // NTT + 1
+    int8_t *lab = reinterpret_cast<int8_t *>(scan + NTT + 1);   // T
     const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
-    const bool act = c < C, producer = c == NT - 1;
     const size_t total_rows = (size_t)T * N;
     const size_t vrow = (size_t)N * R::VP;
-    const float *abase = alpha + (size_t)n * R::VP, *bbase = beta + (size_t)n * R::VP, *mbase = bmax + (size_t)n * R::VP;
-    auto fetch = [&](int t) {
-        const int slot = t % D;
-        const size_t rid = (size_t)t * N + n;
-        xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + 3 * R::VECB);
-        R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
-        bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
-        bulk_g2s(xbptx::smem_u32(ringB + slot * R::VP), bbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
-        bulk_g2s(xbptx::smem_u32(ringM + slot * R::VP), mbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
-    };
-    if (producer) {
-        for (int j = 0; j < D; j++) xbptx::mbar_init(&full[j], 1);
+    if (c == NT) {
+        for (int j = 0; j < D; j++) { xbptx::mbar_init(&full[j], 1); xbptx::mbar_init(&empty[j], W); xbptx::mbar_init(&cand[j], W); }
         xbptx::fence_barrier_init();
     }
-    am[c] = act ? 1.0f : 0.0f;
-    if (lane == 0) redm[w] = 1.0f;
+    if (c < NT) {
+        am[c] = c < C ? 1.0f : 0.0f;
+        if (lane == 0) redm[w] = 1.0f;
+    }
     __syncthreads();
-    if (producer)
-        for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
-    int src[NZ];
-    src[0] = act ? c : 0;
+    if (w == W) {                            // ---------------- service warp: copies ahead, labels behind
+        if (lane == 0) {
+            const float *abase = alpha + (size_t)n * R::VP, *bbase = beta + (size_t)n * R::VP, *mbase = bmax + (size_t)n * R::VP;
+            auto fetch = [&](int t) {
+                const int slot = t % D;
+                const size_t rid = (size_t)t * N + n;
+                xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + 3 * R::VECB);
+                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
+                bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
+                bulk_g2s(xbptx::smem_u32(ringB + slot * R::VP), bbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
+                bulk_g2s(xbptx::smem_u32(ringM + slot * R::VP), mbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
+            };
+            for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
+            for (int t = 0; t < T; t++) {
+                if (t + D - 1 < T) {
+                    if (t > 0) service_wait(&empty[(t - 1) % D], ((t - 1) / D) & 1);
+                    fetch(t + D - 1);
+                }
+                // label of step t: first flat edge index among the per-warp maxima
+                const int q = t % D;
+                service_wait(&cand[q], (t / D) & 1);
+                float bv = bval[q * W];
+                int bi = bidx[q * W];
 #pragma unroll
-    for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
-
-    const size_t prow = (size_t)N * S;
-    float *pout = POST ? post_out + (size_t)n * S + c * NZ : nullptr;
-    for (int t = 0; t < T; t++) {
-        const int slot = t % D;
-        xbptx::mbar_wait(&full[slot], (t / D) & 1);
-        __syncthreads();
-        if (producer && t + D - 1 < T) fetch(t + D - 1);
-        if (c == 0 && t > 0) {           // finish step t-1: reduce the per-warp candidates
-            const int q = (t - 1) & 1;
-            float bv = bval[q * W];
-            int bi = bidx[q * W];
-            for (int j = 1; j < W; j++) {
-                float v = bval[q * W + j];
-                int ix = bidx[q * W + j];
-                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+                for (int j = 1; j < W; j++) {
+                    const float v = bval[q * W + j];
+                    const int ix = bidx[q * W + j];
+                    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+                }
+                lab[t] = (int8_t)(bi % NZ);
             }
-            lab[t - 1] = (int8_t)(bi % NZ);
         }
-        const float sc = xb_pow2_scale(red_max<W>(redm + (t & 1) * W));
-        const float inv = XB_RCP(ringB[slot * R::VP + NT]);
-        const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n) + c * NZ;
-        const float *A = ringA + slot * R::VP;
-        const float *ac = am + (t & 1) * NT;
-        float best = 0.0f, m = 0.0f;
-        int besti = 0x7fffffff;
-        if (act) {
-            const float bc = ringB[slot * R::VP + c], mc = ringM[slot * R::VP + c];
+    } else {
+        const bool act = c < C;
+        int src[NZ];
+        src[0] = act ? c : 0;
 #pragma unroll
-            for (int k = 0; k < NZ; k++) {
-                const float we = XB_MUL(edge_E<LIN>(M[k]), bc);
-                const float p = XB_MUL(XB_MUL(A[src[k]], we), inv);
-                if (POST) pout[k] = p;
-                const float v = XB_MUL(XB_ADD(p, XB_POST_EPS), XB_MUL(ac[src[k]], sc));
-                m = (k == 0) ? v : fmaxf(m, v);
-                const float cand = XB_MUL(v, mc);
-                if (k == 0 || cand > best) { best = cand; besti = c * NZ + k; }
+        for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
+        const size_t prow = (size_t)N * S;
+        float *pout = POST ? post_out + (size_t)n * S + c * NZ : nullptr;
+        for (int t = 0; t < T; t++) {
+            const int slot = t % D;
+            xbptx::mbar_wait(&full[slot], (t / D) & 1);
+            compute_bar(NT);
+            const float sc = xb_pow2_scale(red_max<W>(redm + (t & 1) * W));
+            const float inv = XB_RCP(ringB[slot * R::VP + NT]);
+            const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n) + c * NZ;
+            const float *A = ringA + slot * R::VP;
+            const float *ac = am + (t & 1) * NT;
+            float best = 0.0f, m = 0.0f;
+            int besti = 0x7fffffff;
+            float ev[NZ], av[NZ], bc = 0.0f, mc = 0.0f;
+            if (act) {                        // everything this step needs from the ring slot, then release it
+#pragma unroll
+                for (int k = 0; k < NZ; k++) { ev[k] = edge_E<LIN>(M[k]); av[k] = A[src[k]]; }
+                bc = ringB[slot * R::VP + c];
+                mc = ringM[slot * R::VP + c];
             }
-            am[((t + 1) & 1) * NT + c] = m;
-        }
-        if (POST) pout += prow;
-        {
+            __syncwarp();
+            if (lane == 0) xbptx::mbar_arrive(&empty[slot]);
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < NZ; k++) {
+                    const float we = XB_MUL(ev[k], bc);
+                    const float p = XB_MUL(XB_MUL(av[k], we), inv);
+                    if (POST) pout[k] = p;
+                    const float v = XB_MUL(XB_ADD(p, XB_POST_EPS), XB_MUL(ac[src[k]], sc));
+                    m = (k == 0) ? v : fmaxf(m, v);
+                    const float cnd = XB_MUL(v, mc);
+                    if (k == 0 || cnd > best) { best = cnd; besti = c * NZ + k; }
+                }
+                am[((t + 1) & 1) * NT + c] = m;
+            }
+            if (POST) pout += prow;
             const float wm = warp_max_pos(m);
             if (lane == 0) redm[((t + 1) & 1) * W + w] = wm;
             // warp arg-max with first-index ties: candidates are non-negative, so their bit patterns order like the values
@@ -377,23 +445,15 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
                 best = __shfl_sync(0xffffffffu, best, src_lane);
                 besti = __shfl_sync(0xffffffffu, besti, src_lane);
             }
-            if (lane == 0) { bval[(t & 1) * W + w] = best; bidx[(t & 1) * W + w] = besti; }
+            if (lane == 0) {
+                bval[slot * W + w] = best;
+                bidx[slot * W + w] = besti;
+                xbptx::mbar_arrive(&cand[slot]);
+            }
         }
     }
     __syncthreads();
-    if (c == 0 && T > 0) {
-        const int q = (T - 1) & 1;
-        float bv = bval[q * W];
-        int bi = bidx[q * W];
-        for (int j = 1; j < W; j++) {
-            float v = bval[q * W + j];
-            int ix = bidx[q * W + j];
-            if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-        }
-        lab[T - 1] = (int8_t)(bi % NZ);
-    }
-    __syncthreads();
-    pack_labels<NT>(lab, scan, T, n, labels_out, seq_out, qs_out, lens_out, abc);
+    pack_labels<NTT>(lab, scan, T, n, labels_out, seq_out, qs_out, lens_out, abc);
 }
 
 template <typename K> int set_smem(xb_handle *h, K kernel, size_t bytes) {
@@ -406,38 +466,39 @@ int lin_impl(xb_handle *h, const float *scores, int T, int N, int8_t *labels, in
              float *post, cudaStream_t s) {
     using L = Lat<NB, SL>;
     using R = Ring<NB, SL>;
+    constexpr int NTT = L::NT + 32;
     XB_REQUIRE(h, (reinterpret_cast<uintptr_t>(scores) & 15) == 0, "scores must be 16-byte aligned");
     // state vectors with pitch VP in handle workspace (xb_create sizes the three buffers for it)
     float *alpha = h->alpha, *beta = h->lp, *bmax = h->bmax;
     {
         xb_stage_timer tm(h, XB_ST_CRF_ALPHA, s);
         auto k = crf_lin_alpha_kernel<NB, SL, LIN>;
-        const size_t sm = sizeof(float) * (L::D * R::ROWF + 2 * L::NT + 2 * L::W + 2) + 8 * L::D;
+        const size_t sm = sizeof(float) * (L::D * R::ROWF + 2 * L::NT + 2 * L::W + 2) + 16 * L::D;
         if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, L::NT, sm, s>>>(scores, T, N, alpha);
+        k<<<N, NTT, sm, s>>>(scores, T, N, alpha);
         XB_LAUNCH_CHECK(h);
     }
     {
         xb_stage_timer tm(h, XB_ST_CRF_BACKWARD, s);
         auto k = crf_lin_backward_kernel<NB, SL, LIN>;
-        const size_t sm = sizeof(float) * (L::D * R::ROWF + L::D * R::VP + 4 * L::NT + 6 * L::W) + 8 * L::D;
+        const size_t sm = sizeof(float) * (L::D * R::ROWF + L::D * R::VP + 4 * L::NT + 6 * L::W + 2) + 16 * L::D;
         if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, L::NT, sm, s>>>(scores, alpha, T, N, beta, bmax);
+        k<<<N, NTT, sm, s>>>(scores, alpha, T, N, beta, bmax);
         XB_LAUNCH_CHECK(h);
     }
     xb_stage_timer tm(h, XB_ST_CRF_VITERBI, s);
-    const size_t sm = sizeof(float) * (L::D * R::ROWF + 3 * L::D * R::VP + 2 * L::NT + 6 * L::W + L::NT + 1) + 8 * L::D +
-                      ((T + 15) / 16) * 16;
+    const size_t sm = sizeof(float) * (L::D * R::ROWF + 3 * L::D * R::VP + 2 * L::NT + 2 * L::W + 2 * L::D * L::W + 2 + NTT + 1) +
+                      24 * L::D + ((T + 15) / 16) * 16;
     Alphabet abc;
     for (int i = 0; i < 16; i++) abc.ch[i] = h->alphabet[i];
     if (post) {
         auto k = crf_lin_viterbi_kernel<NB, SL, LIN, true>;
         if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, L::NT, sm, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, post, abc);
+        k<<<N, NTT, sm, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, post, abc);
     } else {
         auto k = crf_lin_viterbi_kernel<NB, SL, LIN, false>;
         if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, L::NT, sm, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, nullptr, abc);
+        k<<<N, NTT, sm, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, nullptr, abc);
     }
     XB_LAUNCH_CHECK(h);
     return XB_OK;
