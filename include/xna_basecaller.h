@@ -138,6 +138,15 @@ int xb_crf_viterbi(xb_handle *h, const float *scores, int T, int N, int8_t *labe
 int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring,
                   int32_t *lens, int8_t *labels_nt, float *post, void *stream);
 
+/* Beam-search decode for any alphabet (the role koi.decode.beam_search plays at crf/basecall.py:33-46; koi itself is
+ * ACGT-only and switched off for the UB models, util.py:299-313): a beam of beam_width <= 32 (emitted sequence, lattice
+ * state) pairs that sums the alignments of a sequence and is guided by the exact backward scores; candidates further than
+ * beam_cut below the leader are dropped.  scores (T, N, C*NZ) fp32 as for xb_crf_decode.  seq / qstring (N, T) int8
+ * left-packed letters and phred+33 qualities, moves (N, T) int8 = 1 at the steps that emitted a base, lens (N);
+ * qstring and moves may be NULL.  Algorithm and its checker: csrc/beam_search.cu, oracle/c/crf_exact.c. */
+int xb_crf_beam_search(xb_handle *h, const float *scores, int T, int N, int beam_width, float beam_cut, int8_t *seq,
+                       int8_t *qstring, int8_t *moves, int32_t *lens, void *stream);
+
 /* The fused route's hand-over format.  decode_batch is computed in the linear domain (sums / maxima of products of
  * E = exp(score), see csrc/crf_decode_lin.cu); when encoder and decode run back to back the CRF head writes E itself
  * -- one bit-reproducible exponential per edge instead of one in each of the three decode sweeps -- and the decode

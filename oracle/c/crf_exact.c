@@ -370,6 +370,110 @@ int xbo_crf_decode_lin_range(const float *scores, int lin_input, int T, int N, i
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Beam search over the CRF lattice: the plain-C statement of xna_basecaller_b200/csrc/beam_search.cu (see the algorithm in
+ * that file's header; koi.decode.beam_search, which the reference calls at crf/basecall.py:33-46, is third-party and
+ * ACGT-only, so this decoder is pinned by brute force in the tests, not against koi).
+ * labels (N,T) int8 (0 = stay, k = move through edge k), quals (N,T) uint8 (phred+33 at emitting steps, else 0). */
+static int beta_rank(const float *b0, int C, int c) {
+    int r = 0;
+    for (int d = 0; d < C; d++) r += (b0[d] > b0[c]) || (b0[d] == b0[c] && d < c);
+    return r;
+}
+
+int xbo_crf_beam_search(const float *scores, int T, int N, int n_base, int state_len, int beam_width, float beam_cut,
+                        int8_t *labels, uint8_t *quals) {
+    lattice L; if (lattice_init(&L, n_base, state_len)) return -1;
+    const int C = L.C, NZ = L.NZ, W = beam_width;
+    if (W < 1 || W > 32 || W * NZ > 256) return -3;
+    size_t S = (size_t)C * NZ;
+    float *beta = (float *)malloc((size_t)(T + 1) * C * sizeof(float));
+    unsigned char *back = (unsigned char *)malloc((size_t)T * 32 + 1);
+    if (!beta || !back) return -2;
+    const unsigned long long FNV = 1099511628211ULL;
+    for (int n = 0; n < N; n++) {
+        for (int c = 0; c < C; c++) beta[(size_t)T * C + c] = 0.0f;
+        for (int t = T - 1; t >= 0; t--)
+            beta_step(&L, scores + ((size_t)t * N + n) * S, beta + (size_t)(t + 1) * C, beta + (size_t)t * C, 0);
+        float bscore[2][32]; int bstate[2][32], istate[32]; unsigned long long bhash[2][32];
+        int nb = W < C ? W : C;
+        for (int c = 0; c < C; c++) {
+            int r = beta_rank(beta, C, c);
+            if (r < W) { bscore[0][r] = 0.0f; bstate[0][r] = c; istate[r] = c; bhash[0][r] = (unsigned long long)c + 1ULL; }
+        }
+        for (int t = 0; t < T; t++) {
+            const int cur = t & 1, nxt = cur ^ 1, ncand = nb * NZ;
+            const float *M = scores + ((size_t)t * N + n) * S, *b1 = beta + (size_t)(t + 1) * C;
+            float cscore[256], ckey[256], lsc[256]; int cstate[256], cfirst[256], alive[256]; unsigned long long chash[256];
+            for (int i = 0; i < ncand; i++) {
+                int e = i / NZ, k = i - e * NZ, s = bstate[cur][e], s2 = s, edge = s * NZ;
+                unsigned long long h = bhash[cur][e];
+                if (k > 0) { s2 = (s % L.n_pow) * L.n + (k - 1); edge = s2 * NZ + 1 + s / L.n_pow; h = h * FNV + (unsigned long long)k; }
+                cscore[i] = XB_ADD(bscore[cur][e], M[edge]); cstate[i] = s2; chash[i] = h;
+            }
+            for (int i = 0; i < ncand; i++) {
+                cfirst[i] = i;
+                for (int j = 0; j < i; j++) if (chash[j] == chash[i] && cstate[j] == cstate[i]) { cfirst[i] = j; break; }
+            }
+            for (int i = 0; i < ncand; i++) {
+                alive[i] = cfirst[i] == i;
+                lsc[i] = XB_NEG_BIG; ckey[i] = XB_NEG_BIG;
+                if (!alive[i]) continue;
+                float m = cscore[i];
+                for (int j = i + 1; j < ncand; j++) if (cfirst[j] == i && cscore[j] > m) m = cscore[j];
+                float ssum = 0.0f; int any = 0;
+                for (int j = i; j < ncand; j++) if (cfirst[j] == i) {
+                    float ex = xb_expf(XB_SUB(cscore[j], m));
+                    ssum = any ? XB_ADD(ssum, ex) : ex; any = 1;
+                }
+                lsc[i] = XB_ADD(m, xb_logf(ssum));
+                ckey[i] = XB_ADD(lsc[i], b1[cstate[i]]);
+            }
+            float best = XB_NEG_BIG;
+            for (int j = 0; j < ncand; j++) if (alive[j] && ckey[j] > best) best = ckey[j];
+            int cnt = 0;
+            for (int i = 0; i < ncand; i++) {
+                if (!alive[i]) continue;
+                int rank = 0;
+                for (int j = 0; j < ncand; j++) if (alive[j]) rank += (ckey[j] > ckey[i]) || (ckey[j] == ckey[i] && j < i);
+                if (rank < W && ckey[i] >= XB_SUB(best, beam_cut)) {
+                    bscore[nxt][rank] = lsc[i]; bstate[nxt][rank] = cstate[i]; bhash[nxt][rank] = chash[i];
+                    back[(size_t)t * 32 + rank] = (unsigned char)((i / NZ) | ((i % NZ) << 5));
+                    cnt++;
+                }
+            }
+            nb = cnt;
+        }
+        int slot = 0;
+        for (int t = T - 1; t >= 0; t--) {
+            unsigned char bk = back[(size_t)t * 32 + slot];
+            labels[(size_t)n * T + t] = (int8_t)(bk >> 5);
+            slot = bk & 31;
+        }
+        int s = istate[slot];          /* forward along the path: new base (b + 1) -> label = edge index 1 + dropped base */
+        for (int t = 0; t < T; t++) {
+            int b1 = labels[(size_t)n * T + t];
+            uint8_t q = 0;
+            if (b1 > 0) {
+                int s2 = (s % L.n_pow) * L.n + (b1 - 1), k = 1 + s / L.n_pow;
+                const float *M = scores + ((size_t)t * N + n) * S;
+                float lp = XB_SUB(XB_ADD(M[s2 * NZ + k], beta[(size_t)(t + 1) * C + s2]), beta[(size_t)t * C + s]);
+                float err = XB_SUB(1.0f, xb_expf(lp));
+                err = err < 1e-5f ? 1e-5f : err;
+                float qf = XB_MUL(-4.34294481903251828f, xb_logf(err));
+                int qi = (int)(XB_ADD(qf, 0.5f));
+                qi = qi < 1 ? 1 : (qi > 50 ? 50 : qi);
+                q = (uint8_t)(33 + qi);
+                labels[(size_t)n * T + t] = (int8_t)k;
+                s = s2;
+            }
+            if (quals) quals[(size_t)n * T + t] = q;
+        }
+    }
+    free(beta); free(back);
+    return 0;
+}
+
 int xbo_crf_posteriors(const float *scores, int T, int N, int n_base, int state_len, float *post) {
     int8_t *lab = (int8_t *)malloc((size_t)N * T);
     if (!lab) return -2;

@@ -139,6 +139,17 @@ def crf_decode_threads(scores, n_base, state_len=3, threads=1):
     return crf_decode(scores, n_base, state_len, threads=threads)
 
 
+def crf_beam_search(scores, n_base, state_len=3, beam_width=32, beam_cut=100.0):
+    """Beam search over the CRF lattice (the contract of csrc/beam_search.cu): labels (N,T) int8, quals (N,T) uint8."""
+    s = _f32(scores)
+    T, N, _ = s.shape
+    labels = np.empty((N, T), dtype=np.int8)
+    quals = np.empty((N, T), dtype=np.uint8)
+    rc = lib().xbo_crf_beam_search(_p(s), T, N, n_base, state_len, int(beam_width), ctypes.c_float(beam_cut), _p(labels), _p(quals))
+    assert rc == 0, rc
+    return labels, quals
+
+
 def crf_viterbi(scores, n_base, state_len=3):
     s = _f32(scores)
     T, N, _ = s.shape

@@ -256,3 +256,49 @@ def test_basecall_restatement_matches_reference_golden(golden):
         assert res['qstring'] == str(g[rid + '_qstring'])
         assert len(res['sig_move']) == int(g[rid + '_sig_move_len'])
         assert not res['sig_move'].any()
+
+
+# ----------------------------------------------------------------------------- beam search
+@pytest.mark.parametrize('T', [1, 2, 3, 5])
+def test_beam_search_finds_the_most_probable_sequence_brute_force(T):
+    """n_base 2, state_len 2: enumerate every path, group the paths by the base sequence they spell (start state, emitted
+    labels, final state -- the last state_len bases are still inside the state), logsumexp per sequence.  The beam search
+    (width 32 < number of sequences from T = 2 on, so it prunes) must return the labels of the most probable sequence."""
+    n, sl = 2, 2
+    crf = bo.CRF(sl, ['N', 'A', 'C'])
+    rs = np.random.RandomState(4 + T)
+    idx = crf.idx.numpy()
+    for _ in range(12):
+        s = rs.uniform(-3, 3, size=(T, 1, crf.C * crf.NZ)).astype(np.float32)
+        Ms = s.reshape(T, crf.C, crf.NZ).astype(np.float64)
+        groups = {}
+        for states in itertools.product(range(crf.C), repeat=T + 1):
+            for edges in itertools.product(range(crf.NZ), repeat=T):
+                if all(idx[states[t + 1], edges[t]] == states[t] for t in range(T)):
+                    w = sum(Ms[t, states[t + 1], edges[t]] for t in range(T))
+                    groups.setdefault((states[0], states[-1]) + tuple(e for e in edges if e), []).append(w)
+        best = max(groups.items(), key=lambda kv: np.logaddexp.reduce(kv[1]))[0]
+        labels, quals = cexact.crf_beam_search(s, n, sl, beam_width=32)
+        assert tuple(int(x) for x in labels[0] if x) == best[2:]
+        assert ((quals[0] > 0) == (labels[0] != 0)).all() and (quals[0][quals[0] > 0] >= 34).all() and quals[0].max() <= 83
+
+
+def test_beam_search_on_confident_scores_equals_viterbi():
+    """Where one path dominates (confident scores) the most probable sequence is the Viterbi path's sequence."""
+    rs = np.random.RandomState(1)
+    T, n_base = 120, 5
+    C, NZ = 125, 6
+    s = np.full((T, 1, C, NZ), -5.0, dtype=np.float32)
+    s[..., 0] = 2.0
+    state = 17
+    for t in range(T):                       # plant a path: stay or move with a large margin
+        if rs.rand() < 0.5:
+            new = (state % 25) * 5 + rs.randint(5)
+            s[t, 0, new, 1 + state // 25] = 5.0
+            state = new
+        else:
+            s[t, 0, state, 0] = 5.0
+    s = s.reshape(T, 1, -1)
+    labels, _ = cexact.crf_beam_search(s, n_base)
+    assert np.array_equal(labels, cexact.crf_viterbi(s, n_base))
+    assert np.array_equal(labels, cexact.crf_decode(s, n_base))

@@ -254,3 +254,22 @@ def test_full_size_properties():
         del s, post
         h.close()
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('n_base,T,N,width', [(5, 400, 6, 32), (6, 300, 4, 32), (4, 500, 5, 16), (5, 50, 3, 1)])
+def test_beam_search_bit_exact_vs_c_oracle(handles, n_base, T, N, width):
+    """xb_crf_beam_search == the plain-C statement of the algorithm (labels via moves / letters, qualities), and its
+    sequences are at least as long-lived as Viterbi's on the same scores (sanity: similar lengths)."""
+    h = handles[n_base]
+    s = synthetic_scores(900 + T, T, N, n_base)
+    seq, qs, moves, lens = h.beam_search(s, beam_width=width, beam_cut=100.0)
+    torch.cuda.synchronize()
+    o_labels, o_quals = cexact.crf_beam_search(s.numpy(), n_base, beam_width=width, beam_cut=100.0)
+    o_seq, _, o_lens = cexact.pack(o_labels, ALPHABETS[n_base])
+    assert np.array_equal(moves.cpu().numpy(), o_labels != 0)
+    assert np.array_equal(seq.cpu().numpy(), o_seq) and np.array_equal(lens.cpu().numpy(), o_lens)
+    for i in range(N):
+        assert np.array_equal(qs[i, :o_lens[i]].cpu().numpy().astype(np.uint8), o_quals[i][o_quals[i] > 0])
+        assert not qs[i, o_lens[i]:].any()
+    vit_lens = h.decode(s, want_qstring=False)[2].cpu().numpy()
+    assert np.abs(lens.cpu().numpy() - vit_lens).max() <= max(8, T // 20)

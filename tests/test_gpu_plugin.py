@@ -245,3 +245,28 @@ def test_bf16_end_to_end_identical_read_rate(golden):
         print('%s: identical-read rate %d/%d vs the fp32 reference path, worst edit rate %.3f, mean length %.0f'
               % (dtype, same, len(want), worst, np.mean([len(v) for v in want.values()])))
         assert worst <= max_rate
+
+
+def test_compute_scores_beam_search_branch():
+    """compute_scores' beam-search branch (crf/basecall.py:33-46: a model built with expand_blanks=False): scores without
+    blank columns, blank score inserted, beam search -> {'sequence', 'qstring', 'moves'} with real qualities and moves."""
+    from xna_basecaller_b200 import util
+    from xna_basecaller_b200.crf.basecall import compute_scores
+    from oracle import cexact
+    cfg = sup_config(ALPHABETS[5])
+    cfg['encoder']['expand_blanks'] = False
+    m = util.load_symbol(cfg, 'Model')(cfg)
+    m.load_state_dict(bo.reference_state_dict(n_base=5, seed=11))
+    m = m.half().eval().to('cuda')
+    x = synthetic_signal(35, 3, 500)
+    out = compute_scores(m, x, beam_width=32, beam_cut=100.0, blank_score=2.0)
+    assert set(out) == {'sequence', 'qstring', 'moves'} and out['moves'].shape == (3, 100) and out['moves'].dtype == bool
+    with torch.no_grad():
+        s = m(x.cuda()).float().cpu()                                   # (T, N, C * n_base): no blank columns
+    full = torch.nn.functional.pad(s.view(100, 3, -1, 5), (1, 0), value=2.0).view(100, 3, -1)
+    labels, quals = cexact.crf_beam_search(full.numpy(), 5)
+    seq, _, lens = cexact.pack(labels, ALPHABETS[5])
+    assert np.array_equal(out['sequence'].numpy(), seq) and np.array_equal(out['moves'], labels != 0)
+    assert int(lens.sum()) > 0
+    q = out['qstring'].numpy()
+    assert ((q != 0) == (seq != 0)).all() and q[q != 0].min() >= 34

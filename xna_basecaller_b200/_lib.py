@@ -26,7 +26,7 @@ SYMBOLS = (
     'xb_ctc_crf_loss_fwd', 'xb_ctc_crf_loss_bwd', 'xb_stitch', 'xb_gather_chunks', 'xb_preprocess_reads', 'xb_compute_scores_host', 'xb_compute_scores_submit', 'xb_compute_scores_wait', 'xb_launch_count', 'xb_gemm_selftest',
     'xb_set_profiling', 'xb_stage_times', 'xb_crf_head_fwd_exp', 'xb_crf_decode_exp', 'xb_basecall_chunks',
     'xb_crf_logz_s', 'xb_crf_forward_scores_s', 'xb_crf_backward_scores_s', 'xb_crf_posteriors_max',
-    'xb_encoder_fwd_train', 'xb_encoder_bwd', 'xb_adamw_step',
+    'xb_encoder_fwd_train', 'xb_encoder_bwd', 'xb_adamw_step', 'xb_crf_beam_search',
 )
 STAGES = ('conv12_im2col', 'conv3_gemm', 'lstm_inproj_gemm', 'lstm_recurrence', 'crf_head_gemm', 'crf_alpha',
           'crf_backward', 'crf_viterbi')
@@ -67,6 +67,7 @@ def load():
     lib.xb_encoder_bwd.argtypes = [vp, vp, ci, vp, vp, ctypes.POINTER(vp), ci, vp]
     lib.xb_adamw_step.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                   ctypes.POINTER(ctypes.c_int64), ci, cf, cf, cf, cf, cf, cf, ctypes.c_int64, vp, vp, vp]
+    lib.xb_crf_beam_search.argtypes = [vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp]
     lib.xb_crf_logz_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_crf_forward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.xb_crf_backward_scores_s.argtypes = [vp, vp, ci, ci, ci, vp, vp]
@@ -366,6 +367,17 @@ class Handle:
         if want_post:
             out.append(post)
         return tuple(out)
+
+    def beam_search(self, scores, beam_width=32, beam_cut=100.0):
+        """(sequence (N,T) int8 left-packed letters, qstring (N,T) int8 phred+33, moves (N,T) bool, lens (N) int32)."""
+        s, T, N = self._scores(scores)
+        seq = torch.empty(N, T, dtype=torch.int8, device=self.device)
+        qs = torch.empty(N, T, dtype=torch.int8, device=self.device)
+        mv = torch.empty(N, T, dtype=torch.int8, device=self.device)
+        lens = torch.empty(N, dtype=torch.int32, device=self.device)
+        self._check(self.lib.xb_crf_beam_search(self.h, _ptr(s), T, N, int(beam_width), float(beam_cut), _ptr(seq), _ptr(qs),
+                                                _ptr(mv), _ptr(lens), _stream(self.device)), 'xb_crf_beam_search')
+        return seq, qs, mv.bool(), lens
 
     def ctc_loss(self, scores, targets, lengths, normalise=True):
         s, T, N = self._scores(scores)

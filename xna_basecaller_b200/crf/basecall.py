@@ -32,12 +32,20 @@ def _pinned(model, name, shape, dtype):
 def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offset=0.0, blank_score=2.0, reverse=False):
     """Compute scores for model: batch (N, 1, chunksize) host tensor -> {'sequence', 'qstring', 'moves'}."""
     head = model.encoder[-1]
-    if not head.expand_blanks:
-        raise RuntimeError('beam search (expand_blanks=False) is koi-only in the reference and is bypassed for UB '
-                           'alphabets (bonito/util.py:299-301); the B200 path decodes with Viterbi')
     device = next(model.parameters()).device
     N, _, L = batch.shape
     T = L // model.stride
+    if not head.expand_blanks:
+        # the reference's beam-search branch (crf/basecall.py:33-46; koi's decoder is ACGT-only, this one takes any alphabet):
+        # scores without blank columns -> blank score inserted (nn.py:122-129) -> xb_crf_beam_search
+        with torch.no_grad():
+            scores = model(batch.to(device)).float()
+        n = head.n_base
+        scores = torch.nn.functional.pad(scores.view(T, N, -1, n), (1, 0, 0, 0, 0, 0, 0, 0), value=blank_score).view(T, N, -1)
+        if reverse:
+            scores = model.seqdist.reverse_complement(scores)
+        seq, qs, moves, _ = model.seqdist.beam_search(scores, beam_width=beam_width, beam_cut=beam_cut)
+        return {'qstring': qs.cpu(), 'sequence': seq.cpu(), 'moves': moves.cpu().numpy()}
     if reverse or batch.device.type != 'cpu':
         # reverse complement permutes the score tensor between encoder and decode: two device calls
         with torch.no_grad():

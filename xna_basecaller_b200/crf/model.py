@@ -114,6 +114,11 @@ class CTC_CRF:
         path = np.asarray(path)
         return letters[path[path != 0]].tobytes().decode()
 
+    def beam_search(self, scores, beam_width=32, beam_cut=100.0):
+        """Beam-search decode (the role of koi.decode.beam_search, which is ACGT-only): (sequence, qstring, moves, lens),
+        sequence / qstring (N, T) int8 left-packed, moves (N, T) bool."""
+        return self._handle(scores).beam_search(scores, beam_width, beam_cut)
+
     def decode_packed(self, scores):
         """decode_batch without the host strings: (seq (N,T) int8 left-packed letters, qstring, lens)."""
         return self._handle(scores).decode(scores)

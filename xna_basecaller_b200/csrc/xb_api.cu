@@ -38,6 +38,8 @@ int xb_stitch_impl(xb_handle *h, const int8_t *rows, int T, const int32_t *chunk
                    int out_stride, int32_t *out_len, cudaStream_t s);
 
 void xb_train_free(xb_handle *h);
+int xb_beam_search_impl(xb_handle *h, const float *scores, const float *beta, int T, int N, int beam_width, float beam_cut,
+                        int8_t *seq, int8_t *qstring, int8_t *moves, int32_t *lens, cudaStream_t s);
 int xb_onehot_edges(xb_handle *h, const int32_t *edges_nt, int T, int N, int S, float *post, cudaStream_t s);
 int xb_gather_chunks_impl(xb_handle *h, const void *signal, int sig_dtype, const int64_t *read_offset,
                           const int32_t *read_len, const int32_t *chunk_read, const int32_t *chunk_start, int n_chunks,
@@ -585,6 +587,15 @@ int xb_crf_decode(xb_handle *h, const float *scores, int T, int N, int8_t *seq, 
     XB_CRF_PROLOGUE();
     XB_REQUIRE(h, seq != nullptr && lens != nullptr, "seq / lens is NULL");
     return xb_decode_lin(h, scores, 0, T, N, labels_nt, seq, qstring, lens, post, s);
+}
+
+// Beam-search decode (csrc/beam_search.cu): Log-semiring backward scores into handle workspace, then the beam
+int xb_crf_beam_search(xb_handle *h, const float *scores, int T, int N, int beam_width, float beam_cut, int8_t *seq,
+                       int8_t *qstring, int8_t *moves, int32_t *lens, void *stream) {
+    XB_CRF_PROLOGUE();
+    XB_REQUIRE(h, seq != nullptr && lens != nullptr, "seq / lens is NULL");
+    if (int rc = xb_decode_backward(h, scores, T, N, nullptr, h->lp, 2, s)) return rc;
+    return xb_beam_search_impl(h, scores, h->lp, T, N, beam_width, beam_cut, seq, qstring, moves, lens, s);
 }
 
 int xb_crf_decode_exp(xb_handle *h, const float *scores, int T, int N, int8_t *seq, int8_t *qstring, int32_t *lens,
