@@ -24,10 +24,15 @@ using namespace xbptx;
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 3;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// Pipeline depth.  Three stages (96 KB) leave room for two CTAs per SM, whose epilogues and main loops overlap.  The
+// one-launch-per-step recurrence GEMMs (a 24-tile grid with K = 3072: one CTA per SM, latency-bound on the TMA round trip)
+// run six stages instead: 192 KB in flight per SM.
+template <int EPI> struct Pipe {
+    static constexpr int STAGES = (EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) ? 6 : 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
@@ -35,6 +40,7 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 template <bool BF16, int EPI>
 __global__ void __launch_bounds__(256, (EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int STAGES = Pipe<EPI>::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -188,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16 *>(p.dy) + cell * XB_FEATURES + u0;
             __nv_bfloat16 *dzp = reinterpret_cast<__nv_bfloat16 *>(p.dz) + cell * XB_GATES + u0;
             float *dcs = p.dcstate + (size_t)m * XB_FEATURES + u0;
-#pragma unroll 1
+#pragma unroll 2
             for (int ub = 0; ub < BN; ub += 8) {
                 uint32_t acc[8];
                 if (kblocks > 0) {
@@ -462,6 +468,7 @@ template <bool BF16, int EPI>
 static int launch_one(xb_handle *h, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, int rows_a,
                       cudaStream_t s) {
     auto k = gemm_tc_kernel<BF16, EPI>;
+    constexpr int SMEM_BYTES = Pipe<EPI>::SMEM_BYTES;
     static bool configured[64] = {};   // per instantiation and device (function attributes live in the context)
     if (!configured[h->device & 63]) {
         XB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
