@@ -12,7 +12,9 @@
  *     text (h may be NULL for errors raised before a handle exists).  Nothing throws, nothing exits.
  *   - a handle is bound to one CUDA device; it owns repacked weights and workspace, all allocated in
  *     xb_create / xb_load_weights.  The caller owns every input/output buffer.  A handle is not
- *     thread-safe; distinct handles are independent.
+ *     thread-safe; distinct handles are independent.  The workspace of a handle (gates, activations,
+ *     decode state vectors, scores of the fused route) is shared by all of its calls: issue them on ONE
+ *     stream, or order streams externally (events) -- nothing inside a handle orders two streams.
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it with no host
  *     synchronisation, except the *_host entry points, which synchronise before returning.
  *   - device pointers unless the parameter name ends in _host.

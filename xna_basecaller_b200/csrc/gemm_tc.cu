@@ -36,6 +36,11 @@ template <int EPI> struct Pipe {
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <bool BF16, int EPI>
 __global__ void __launch_bounds__(256, (EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) ? 1 : 2)
@@ -344,9 +349,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 16; j++) {
                         float v0 = __uint_as_float(acc[2 * j]) + __ldg(p.bias + nb + 2 * j);
                         float v1 = __uint_as_float(acc[2 * j + 1]) + __ldg(p.bias + nb + 2 * j + 1);
-                        if constexpr (EPI == EPI_CONV3) {
-                            v0 = v0 * fast_sigmoid(v0);
-                            v1 = v1 * fast_sigmoid(v1);
+                        if constexpr (EPI == EPI_CONV3) {      // swish with ONE MUFU per element: sigmoid(x) = 0.5 tanh(0.5 x) + 0.5
+                            v0 = v0 * fmaf(tanh_approx(0.5f * v0), 0.5f, 0.5f);      // (the exp + reciprocal form kept this epilogue,
+                            v1 = v1 * fmaf(tanh_approx(0.5f * v1), 0.5f, 0.5f);      // and with it the conv3 GEMM, MUFU-bound)
                         }
                         pk[j] = X::pack(v0, v1);
                     }
