@@ -270,3 +270,41 @@ def test_compute_scores_beam_search_branch():
     assert int(lens.sum()) > 0
     q = out['qstring'].numpy()
     assert ((q != 0) == (seq != 0)).all() and q[q != 0].min() >= 34
+
+
+def test_read_set_pipeline_reverse_and_lazy_stream(model5):
+    """(1) ReadSetBasecaller(reverse=True) (device-side reverse stitch, scores reverse-complemented between encoder and
+    decode) gives the strings of the reference-shaped basecall(..., reverse=True); (2) basecall_reads is LAZY: it pulls
+    reads from the iterator block by block (crf/basecall.py:96-119 hands its consumer an iterator, not a list) and yields
+    results in input order while later blocks have not been pulled yet."""
+    from xna_basecaller_b200 import pipeline
+    from xna_basecaller_b200.crf import basecall
+
+    class Read:
+        def __init__(self, rid, sig):
+            self.read_id, self.signal = rid, sig
+
+    rs = np.random.RandomState(8)
+    lengths = [700, 1000, 2350, 1900, 3100, 999, 4600, 2800, 1001, 1500]
+    sigs = [rs.randn(L).astype(np.float32) for L in lengths]
+    want = [res['sequence'] for _, res in basecall(model5, iter([Read(i, s) for i, s in enumerate(sigs)]),
+                                                   chunksize=1000, overlap=100, batchsize=4, reverse=True)]
+    got, _ = pipeline.ReadSetBasecaller(model5, chunksize=1000, overlap=100, batchsize=7, reverse=True).basecall(sigs)
+    assert got == want and any(len(s) > 0 for s in got)
+
+    pulled = []
+
+    def source():
+        for i, s in enumerate(sigs):
+            pulled.append(i)
+            yield Read(i, s)
+
+    fwd = [res['sequence'] for _, res in basecall(model5, iter([Read(i, s) for i, s in enumerate(sigs)]),
+                                                  chunksize=1000, overlap=100, batchsize=4)]
+    out = pipeline.basecall_reads(model5, source(), chunksize=1000, overlap=100, batchsize=7, block_reads=3)
+    first_read, first = next(out)
+    assert first_read.read_id == 0 and first['sequence'] == fwd[0]
+    assert len(pulled) <= 9, 'the whole iterator was consumed before the first result came out: %s' % pulled
+    rest = [(r.read_id, res['sequence']) for r, res in out]
+    assert [i for i, _ in rest] == list(range(1, len(sigs))) and [s for _, s in rest] == fwd[1:]
+    assert first['qstring'] == 'O' * len(first['sequence']) and not first['sig_move'].any()
