@@ -88,6 +88,7 @@ struct PLParams {
     int one_release;            // 1: one MEMBAR + counter update per sub-batch and step, 0: one per epilogue warp
     int prefetch_y;             // d > 0: prefetch the y rows of step s+d into L2
     long long *dbg;             // optional timeline (XB_EXPERIMENTS, XB_LSTM_DEBUG=1): clock64 stamps of CTA 0, sub-batch 0
+    int tma_store;              // XB_EXPERIMENTS: 1 / 2 = full sub-batches publish h through a TMA tensor store (release / relaxed counter)
     uint16_t *save;             // training forward (SAVE kernels): (T, N, 5, 768) fp16 = activated i, f, g, o and the cell state c
 };
 
@@ -132,7 +133,8 @@ template <> __device__ __forceinline__ void tmem_ld_16x256b<4>(uint32_t taddr, u
 }
 template <bool BF16, int SUB, int NS, int EW, int GB, bool SAVE = false>
 __global__ void __launch_bounds__(Cfg<SUB, NS, EW, GB>::THREADS, 1)
-lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG, const PLParams p) {
+lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
+                       const __grid_constant__ CUtensorMap tmS, const PLParams p) {
     using X = xb16<BF16>;
     using C = Cfg<SUB, NS, EW, GB>;
     extern __shared__ uint8_t smem_raw[];
@@ -152,10 +154,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int g = blockIdx.x / TILES, j = blockIdx.x % TILES;
     const int T = p.T, N = p.N;
-    const int b0 = p.batch0 + (int)(((long long)g * p.nbatch) / p.G);
-    const int b1 = p.batch0 + (int)(((long long)(g + 1) * p.nbatch) / p.G);
+    // Groups take whole sub-batches of NS chunks (units): every sub-batch but the batch's last is full, which lets a full
+    // sub-batch publish its h tile with ONE TMA store (a box of NS rows); the step time is set by the chain latency, not by
+    // the number of chains per SM, so groups of two and of three sub-batches cost the same.
+    const int units = (p.nbatch + NS - 1) / NS;
+    const int b0 = p.batch0 + NS * (int)(((long long)g * units) / p.G);
+    const int b1 = min(p.batch0 + p.nbatch, p.batch0 + NS * (int)(((long long)(g + 1) * units) / p.G));
     const int count = b1 - b0;               // <= NB valid chunks in this group
-    auto sub_row0 = [&](int sub) { return b0 + (sub * count) / SUB; };
+    auto sub_row0 = [&](int sub) { return b0 + sub * NS; };
+    auto sub_cnt = [&](int sub) { return max(0, min(NS, count - sub * NS)); };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY);
@@ -207,15 +214,17 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         if (elect_one()) {
             const int sub = warp;
             const int row0 = sub_row0(sub);
-            const int cnt_sub = b0 + ((sub + 1) * count) / SUB - row0;
+            const int cnt_sub = sub_cnt(sub);
             const int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
             uint8_t *hb = hbuf + sub * C::H_BYTES;
             constexpr uint32_t idesc = umma_idesc_f16(BF16 ? 1u : 0u, 128, NS);
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(hb));
             const uint32_t dcol = tmem_base + D_COL + sub * NS;
-            mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
-            tma_load_2d(gbuf + (sub * GB) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
-            for (int s = 0; s < T; s++) {
+            if (cnt_sub > 0) {
+                mbar_expect_tx(g_full(sub, 0), C::G_BYTES);
+                tma_load_2d(gbuf + (sub * GB) * C::G_BYTES, &tmG, g_full(sub, 0), j * 128, (p.reverse ? T - 1 : 0) * N + row0);
+            }
+            for (int s = 0; s < (cnt_sub > 0 ? T : 0); s++) {      // an empty sub-batch (a short last group) has no chain
                 const int t = p.reverse ? T - 1 - s : s;
                 if (GB == 2 && s + 1 < T) {      // input projection of the next step, one step ahead
                     const int sn = s + 1, q = sn & 1, u = sn >> 1;
@@ -290,14 +299,24 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
         const int gt = lane & 3, ul = lane >> 2;             // gate held after the TMEM load; unit within the warp
         const int unit = q * 8 + ul;                         // unit within the tile
         const int row0 = sub_row0(sub);
-        const int cnt = b0 + ((sub + 1) * count) / SUB - row0;   // valid chunks of this sub-batch (<= NS)
+        const int cnt = sub_cnt(sub);                            // valid chunks of this sub-batch (<= NS)
+        // Round-2 experiment (XB_EXPERIMENTS builds, XB_TMAS=1|2): a FULL sub-batch publishes its h tile through the async
+        // proxy -- staged as a dense [NS chunks][32 units] tile, ONE TMA tensor store, cp.async.bulk.wait_group for its
+        // completion, then the counter.  With a release on the counter it is as fast as the generic route below (14.1 ms per
+        // batch); with a relaxed add it is 8-10 % faster (12.5-13.1 ms), but then nothing orders the tile's writes before the
+        // counter in the PTX memory model, so the product publishes through generic stores + red.release.
+#ifdef XB_EXPERIMENTS
+        const bool tma_store = !SAVE && GB == 2 && cnt == NS && p.tma_store;
+#else
+        constexpr bool tma_store = false;
+#endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + D_COL + sub * NS + col0;
         int *ctr = p.counters + (g * SUB + sub) * CTR_STRIDE;
         float cst[CELLS];
 #pragma unroll
         for (int i = 0; i < CELLS; i++) cst[i] = 0.0f;
 
-        for (int s = 0; s < T; s++) {
+        for (int s = 0; s < (cnt > 0 ? T : 0); s++) {
             const int t = p.reverse ? T - 1 - s : s;
             const uint16_t *Gs = reinterpret_cast<const uint16_t *>(gbuf + (sub * GB + (GB == 2 ? (s & 1) : 0)) * C::G_BYTES);
             // Accumulator -> registers with tcgen05.ld.16x256b: thread (a = lane/4, b = lane%4) receives rows a, a+8 (first
@@ -400,6 +419,32 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             if (GB == 1) __syncwarp();                           // every lane has taken its G values
             // explicit shared-memory instructions: behind the casts the compiler falls back to generic loads / stores
             const uint32_t st_s = smem_u32(st);
+            if (tma_store) {
+                const uint32_t tile_s = smem_u32(stage + sub * (NS * 64));       // [chunk][32 units] fp16, 64 B per chunk
+#pragma unroll
+                for (int i = 0; i < CELLS; i++) {
+                    typename X::T hv = X::from(hout[i]);
+                    sts_u16(tile_s + 2u * ((col0 + 8 * (i >> 1) + 2 * gt + (i & 1)) * 32 + q * 8 + ul), *reinterpret_cast<uint16_t *>(&hv));
+                }
+                fence_proxy_async();                             // my tile bytes -> visible to the async proxy
+                named_bar_sync(1 + sub, EW * 32);
+                if (ew == 0 && lane == 0) {
+                    tma_store_2d(&tmS, tile_s, j * 32, t * N + row0);
+                    bulk_commit_group();
+                    bulk_wait_group0();                          // the tile's writes are complete (acknowledged by L2)
+                    // Release, not relaxed: wait_group makes the async-proxy writes visible to THIS thread; the consumers'
+                    // acquire needs a release pattern to synchronise with.  The MEMBAR.GPU inside costs ~1 ms per batch
+                    // even with no generic store pending (XB_EXPERIMENTS, XB_TMAS=2 publishes relaxed: 12.5-13.1 ms
+                    // per batch instead of 14.1 -- physically the same, outside the memory model).
+#ifdef XB_EXPERIMENTS
+                    if (p.tma_store >= 2) red_relaxed_gpu_add(ctr, EW); else
+#endif
+                    red_release_gpu_add(ctr, EW);
+                    DBG(sub, 13);
+                }
+                if (lane == 0) mbar_arrive(g_empty(sub, s & 1));
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < CELLS; i++) {
                 typename X::T hv = X::from(hout[i]);
@@ -455,8 +500,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
 template <bool BF16, int SUB, int NS, int EW, int GB = 2, bool SAVE = false>
 int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s, void *save = nullptr) {
     using C = Cfg<SUB, NS, EW, GB>;
-    CUtensorMap tmY, tmG;
+    CUtensorMap tmY, tmG, tmS;
     if (int rc = xb_make_tmap_hview(h, &tmY, y_tnc, (uint64_t)T * N, NS, KPB)) return rc;
+    if (int rc = xb_make_tmap_2d_box(h, &tmS, y_tnc, (uint64_t)T * N, XB_FEATURES, XB_FEATURES, 32, NS, 0)) return rc;
     if (int rc = xb_make_tmap_2d_box(h, &tmG, h->gates, (uint64_t)T * N, XB_GATES, XB_GATES, 128, NS, 0)) return rc;
     const int max_groups = h->num_sms / TILES;                 // 6 on a 148-SM B200
     if (max_groups < 1)
@@ -481,13 +527,17 @@ int launch_cfg(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, 
         p.prefetch_y = 4;
         p.dbg = nullptr;
         p.save = reinterpret_cast<uint16_t *>(save);
+        p.tma_store = 0;
+#ifdef XB_EXPERIMENTS
+        if (getenv("XB_TMAS")) p.tma_store = atoi(getenv("XB_TMAS"));
+#endif
 #ifdef XB_EXPERIMENTS
         if (getenv("XB_LSTM_WARP_RELEASE")) p.one_release = 0;
         if (getenv("XB_LSTM_PREFETCH_Y")) p.prefetch_y = atoi(getenv("XB_LSTM_PREFETCH_Y"));
         if (getenv("XB_LSTM_DEBUG")) p.dbg = reinterpret_cast<long long *>(h->lstm_counters + MAX_CTRS * CTR_STRIDE);
 #endif
         XB_CUDA(h, cudaMemsetAsync(h->lstm_counters, 0, MAX_CTRS * CTR_STRIDE * sizeof(int), s));
-        void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&p};
+        void *args[] = {(void *)&tmY, (void *)&tmG, (void *)&tmS, (void *)&p};
         XB_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, dim3(p.G * TILES), dim3(C::THREADS), args, C::SMEM_BYTES, s));
         h->launches++;
     }
