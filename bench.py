@@ -169,12 +169,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def calibrated_weights(h, bo, x_dev, seed=25):
+def calibrated_weights(h, bo, x_dev, seed=25, gain=None):
     """Random-init weights of the sup@v3.3 architecture whose CRF head gain is calibrated so that decodes MIX blanks and
     moves (a plain random-init head decodes every chunk to the empty string, a strongly amplified one emits a base
     at every step; either way left-packing and stitching would have nothing to do).  Returns (state_dict, gain, mean length)."""
     sd = bo.reference_state_dict(n_base=N_BASE, seed=seed)
     w0 = sd['encoder.9.linear.weight'].clone()
+    if gain is not None:                             # --head-gain: skip the calibration (profiling runs)
+        sd['encoder.9.linear.weight'] = w0 * gain
+        h.load_weights(sd)
+        return sd, gain, float('nan')
     lo, hi, best = 0.02, 8.0, None                   # decoded length grows with the gain: bisect in log space
     for _ in range(12):
         gain = (lo * hi) ** 0.5
@@ -267,7 +271,7 @@ def run_readset(args, rank, world, local):
     caller = pipeline.ReadSetBasecaller(model.half().eval().to(dev), CHUNK, 500, args.batch)
     h = caller._handle(args.batch)
     x_cal = torch.randn(64, CHUNK, generator=torch.Generator().manual_seed(5)).to(dev)
-    sd, gain, _ = calibrated_weights(h, bo, x_cal)
+    sd, gain, _ = calibrated_weights(h, bo, x_cal, gain=args.head_gain)
     caller.model.load_state_dict(sd)
     caller.model.half()
     caller._handle(args.batch)
@@ -362,6 +366,7 @@ def main():
                     help='chunks: BASELINE configs[1] (default, weak scaling); readset: configs[3] (strong scaling)')
     ap.add_argument('--reads', type=int, default=100000)
     ap.add_argument('--block-reads', type=int, default=1024)
+    ap.add_argument('--head-gain', type=float, default=None, help='skip the head-gain calibration and use this gain')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-comparator', action='store_true')
     args = ap.parse_args()
@@ -389,7 +394,7 @@ def main():
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(N, L, generator=g).pin_memory()
     x_dev = x_host.to(dev)
-    sd, head_gain, _ = calibrated_weights(h, bo, x_dev)
+    sd, head_gain, _ = calibrated_weights(h, bo, x_dev, gain=args.head_gain)
     seq_host = torch.empty(N, T, dtype=torch.int8).pin_memory()
     lens_host = torch.empty(N, dtype=torch.int32).pin_memory()
     seq_dev = torch.empty(N, T, dtype=torch.int8, device=dev)
