@@ -70,26 +70,21 @@ template <int NB, int SL> struct Ring {
     static constexpr int VECB = VP * 4;
     // float offset of row `rid` (= t * N + n) inside its slot
     static __device__ __forceinline__ int phase(size_t rid) { return PHASED ? (int)(rid & 1) * 2 : 0; }
-    // issue the copy of row rid into `slot` (elected thread); total_rows guards the 8 bytes past the tensor's end
+    // Arm the slot's barrier for the row + `extra_tx` bytes of state vectors and issue the row copy (elected thread).
+    // total_rows guards the 8 bytes past the tensor's end: the last row of the tensor in phase 0 is copied 8 bytes short and
+    // its tail moved by hand -- BEFORE the arrive, whose release orders that generic store ahead of the consumers' wait.
     static __device__ __forceinline__ void fetch_row(float *slot, const float *scores, size_t rid, size_t total_rows,
-                                                     uint64_t *bar) {
+                                                     uint64_t *bar, uint32_t extra_tx) {
         const char *src = reinterpret_cast<const char *>(scores) + rid * ROWB;
-        if (PHASED) {
-            if (rid & 1) {
-                bulk_g2s(xbptx::smem_u32(slot), src - 8, ROW_COPY, bar);
-            } else if (rid + 1 == total_rows) {          // last row of the tensor in phase 0: its 16-byte tail straddles the end
-                bulk_g2s(xbptx::smem_u32(slot), src, ROWB - 8, bar);
-                const float2 tail = *reinterpret_cast<const float2 *>(src + ROWB - 8);
-                *reinterpret_cast<float2 *>(reinterpret_cast<char *>(slot) + ROWB - 8) = tail;
-            } else {
-                bulk_g2s(xbptx::smem_u32(slot), src, ROW_COPY, bar);
-            }
-        } else {
-            bulk_g2s(xbptx::smem_u32(slot), src, ROW_COPY, bar);
+        if (PHASED && !(rid & 1) && rid + 1 == total_rows) {
+            const float2 tail = *reinterpret_cast<const float2 *>(src + ROWB - 8);
+            *reinterpret_cast<float2 *>(reinterpret_cast<char *>(slot) + ROWB - 8) = tail;
+            xbptx::mbar_expect_tx(bar, ROWB - 8 + extra_tx);
+            bulk_g2s(xbptx::smem_u32(slot), src, ROWB - 8, bar);
+            return;
         }
-    }
-    static __device__ __forceinline__ uint32_t row_tx(size_t rid, size_t total_rows) {
-        return (PHASED && !(rid & 1) && rid + 1 == total_rows) ? ROWB - 8 : ROW_COPY;
+        xbptx::mbar_expect_tx(bar, ROW_COPY + extra_tx);
+        bulk_g2s(xbptx::smem_u32(slot), (PHASED && (rid & 1)) ? src - 8 : src, ROW_COPY, bar);
     }
 };
 
@@ -141,8 +136,7 @@ crf_lin_alpha_kernel(const float *__restrict__ scores, int T, int N, float *__re
         if (lane == 0) {
             auto fetch = [&](int r) {
                 const size_t rid = (size_t)r * N + n;
-                xbptx::mbar_expect_tx(&full[r % D], R::row_tx(rid, total_rows));
-                R::fetch_row(ring + (r % D) * R::ROWF, scores, rid, total_rows, &full[r % D]);
+                R::fetch_row(ring + (r % D) * R::ROWF, scores, rid, total_rows, &full[r % D], 0);
             };
             for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
             for (int t = 0; t + D - 1 < T; t++) {
@@ -233,8 +227,7 @@ crf_lin_backward_kernel(const float *__restrict__ scores, const float *__restric
             auto fetch = [&](int r) {        // iteration r: score row and a_hat of step T-1-r
                 const int t = T - 1 - r, slot = r % D;
                 const size_t rid = (size_t)t * N + n;
-                xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + R::VECB);
-                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
+                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot], R::VECB);
                 bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
             };
             for (int j = 0; j < D - 1 && j < T; j++) fetch(j);
@@ -367,8 +360,7 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
             auto fetch = [&](int t) {
                 const int slot = t % D;
                 const size_t rid = (size_t)t * N + n;
-                xbptx::mbar_expect_tx(&full[slot], R::row_tx(rid, total_rows) + 3 * R::VECB);
-                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot]);
+                R::fetch_row(ring + slot * R::ROWF, scores, rid, total_rows, &full[slot], 3 * R::VECB);
                 bulk_g2s(xbptx::smem_u32(ringA + slot * R::VP), abase + (size_t)t * vrow, R::VECB, &full[slot]);
                 bulk_g2s(xbptx::smem_u32(ringB + slot * R::VP), bbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
                 bulk_g2s(xbptx::smem_u32(ringM + slot * R::VP), mbase + (size_t)(t + 1) * vrow, R::VECB, &full[slot]);
