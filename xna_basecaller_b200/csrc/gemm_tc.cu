@@ -448,6 +448,27 @@ int xb_make_tmap_2d_box(xb_handle *h, CUtensorMap *out, const void *base, uint64
     return XB_OK;
 }
 
+// rank-n form (n <= 5): dims / box in elements (innermost first), strides in BYTES for dimensions 1 .. n-1, 128B swizzle
+// (the innermost box extent must span 128 bytes); elem_bytes 2 (16-bit payload) or 4 (fp32)
+int xb_make_tmap_nd(xb_handle *h, CUtensorMap *out, const void *base, int rank, int elem_bytes, const uint64_t *dims,
+                    const uint64_t *strides_bytes, const uint32_t *box) {
+    if (!h->encode_tiled) {
+        CUtensorMap tmp;
+        if (int rc = xb_make_tmap_2d(h, &tmp, base, 128, 64, 64)) return rc;        // resolves the entry point
+    }
+    if (rank < 2 || rank > 5 || (elem_bytes != 2 && elem_bytes != 4)) return xb_fail(h, XB_ERR_ARG, "tensor map rank %d / element size %d", rank, elem_bytes);
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+    CUresult r = reinterpret_cast<encode_tiled_fn>(h->encode_tiled)(
+        out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+        const_cast<void *>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return xb_fail(h, XB_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+    return XB_OK;
+}
+
 // 3-D view of a (rows, 768) 16-bit activation matrix for the persistent LSTM: dims {64 k, rows, 12 k-blocks},
 // strides {1536 B, 128 B}, box {64, box_rows, box_kblocks}, 128B swizzle: one TMA lands box_kblocks K-major
 // [box_rows x 128 B] tiles.

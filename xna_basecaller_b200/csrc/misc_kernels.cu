@@ -176,10 +176,25 @@ __global__ void ctc_simple_bwd_kernel(const float *__restrict__ scores, int T, i
     float *aw = alpha_ws + (size_t)n * npos;
     a[j] = (j == 0) ? 0.0f : XB_NEG_BIG;
     if (act) aw[j] = a[j];
+    // Every global read of a step (score row, stored alpha, incoming gradient row) is issued one step ahead into registers,
+    // so the three L2 / HBM round trips of a step overlap the previous step's arithmetic instead of following each other.
+    constexpr int RPT = 4;                           // row elements per thread: S <= RPT * NT is checked by the launcher
+    float rpre[RPT];
+    auto fetch_row = [&](int t) {
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int e = j + k * NT;
+            rpre[k] = (e < S) ? base[(size_t)t * row + e] : 0.0f;
+        }
+    };
+    fetch_row(0);
     __syncthreads();
     for (int t = 0; t < T; t++) {
-        for (int i = j; i < S; i += NT) rowbuf[i] = base[(size_t)t * row + i];
+#pragma unroll
+        for (int k = 0; k < RPT; k++)
+            if (j + k * NT < S) rowbuf[j + k * NT] = rpre[k];
         __syncthreads();
+        if (t + 1 < T) fetch_row(t + 1);
         const float *ac = a + (t & 1) * NT;
         float *an = a + ((t + 1) & 1) * NT;
         float v = XB_NEG_BIG;
@@ -198,20 +213,45 @@ __global__ void ctc_simple_bwd_kernel(const float *__restrict__ scores, int T, i
     const float scale = grad_loss[n] / (float)len;
     __syncthreads();
     a[j] = (j == last) ? 0.0f : XB_NEG_BIG;           // beta_T in buffer 0
+    float gpre[RPT], at_pre = 0.0f, am1_pre = 0.0f;
+    auto fetch_step = [&](int t) {
+        fetch_row(t);
+        if (normalise) {
+            const float *g = grad + ((size_t)t * N + n) * S;
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                const int e = j + k * NT;
+                gpre[k] = (e < S) ? g[e] : 0.0f;
+            }
+        }
+        if (act) {
+            at_pre = aw[(size_t)t * arow + j];
+            if (j > 0) am1_pre = aw[(size_t)t * arow + j - 1];
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < RPT; k++) gpre[k] = 0.0f;
+    fetch_step(T - 1);
     for (int i = 0; i < T; i++) {
         const int t = T - 1 - i;
-        for (int e = j; e < S; e += NT) { rowbuf[e] = base[(size_t)t * row + e]; acc[e] = 0.0f; }
+        float gcur[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int e = j + k * NT;
+            if (e < S) { rowbuf[e] = rpre[k]; acc[e] = 0.0f; }
+            gcur[k] = gpre[k];
+        }
+        const float at = at_pre, am1 = am1_pre;
         __syncthreads();
+        if (t > 0) fetch_step(t - 1);
         const float *b1 = a + (i & 1) * NT;
         float *b0 = a + ((i + 1) & 1) * NT;
         float bnew = XB_NEG_BIG;
         if (act) {
-            const float at = aw[(size_t)t * arow + j];
             const float stay_term = XB_ADD(XB_SUB(rowbuf[stay_idx], shift), b1[j]);
             if (feasible) {
                 atomicAdd(&acc[stay_idx], xb_expf(XB_SUB(XB_ADD(at, stay_term), lz)));
                 if (j > 0) {
-                    const float am1 = aw[(size_t)t * arow + j - 1];
                     const float mterm = XB_ADD(XB_SUB(rowbuf[move_in], shift), b1[j]);
                     atomicAdd(&acc[move_in], xb_expf(XB_SUB(XB_ADD(am1, mterm), lz)));
                 }
@@ -222,7 +262,11 @@ __global__ void ctc_simple_bwd_kernel(const float *__restrict__ scores, int T, i
         b0[j] = bnew;
         __syncthreads();
         float *g = grad + ((size_t)t * N + n) * S;
-        for (int e = j; e < S; e += NT) g[e] = scale * ((normalise ? g[e] : 0.0f) - acc[e]);
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            const int e = j + k * NT;
+            if (e < S) g[e] = scale * (gcur[k] - acc[e]);
+        }
         __syncthreads();
     }
 }
@@ -284,8 +328,10 @@ int xb_ctc_loss_bwd_impl(xb_handle *h, const float *scores, int T, int N, const 
                          cudaStream_t s) {
     const int npos = Lmax - (h->state_len - 1);
     XB_REQUIRE(h, npos >= 1 && npos <= 1024, "Lmax=%d unsupported (1 <= Lmax-state_len+1 <= 1024)", Lmax);
-    const int NT = ((npos + 31) / 32) * 32;
     const int S = h->C * h->NZ;
+    int NT = ((npos + 31) / 32) * 32;
+    if (NT * 4 < S) NT = ((S + 127) / 128) * 32;      // the kernel keeps a score row in four registers per thread
+    XB_REQUIRE(h, NT <= 1024, "score rows of %d elements are not supported by the loss backward", S);
     size_t smem = sizeof(float) * (3 * NT + 1 + 2 * S);
     if (smem > 48 * 1024)
         XB_CUDA(h, cudaFuncSetAttribute(ctc_simple_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

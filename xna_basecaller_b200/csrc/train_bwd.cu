@@ -255,20 +255,105 @@ int alloc(xb_handle *h, void **p, size_t bytes) {
     return XB_OK;
 }
 
-int transpose_to_bf16(xb_handle *h, const void *in, int R, int C, int ld_in, bool in_bf16, void *out, cudaStream_t s) {
-    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-    if (in_bf16) transpose16_kernel<true><<<grid, block, 0, s>>>(reinterpret_cast<const uint16_t *>(in), R, C, ld_in, reinterpret_cast<__nv_bfloat16 *>(out));
-    else transpose16_kernel<false><<<grid, block, 0, s>>>(reinterpret_cast<const uint16_t *>(in), R, C, ld_in, reinterpret_cast<__nv_bfloat16 *>(out));
-    XB_LAUNCH_CHECK(h);
-    return XB_OK;
-}
-
 int colsum(xb_handle *h, const void *in, int R, int C, int ld, float *out, cudaStream_t s) {
     XB_CUDA(h, cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), s));
     int slabs = (R + 2047) / 2048;
     if (slabs > 256) slabs = 256;
     colsum_kernel<<<dim3((C + 31) / 32, slabs), dim3(32, 8), 0, s>>>(reinterpret_cast<const __nv_bfloat16 *>(in), R, C, ld, out);
     XB_LAUNCH_CHECK(h);
+    return XB_OK;
+}
+
+// Vector form of the same transposition for shapes whose rows are 16-byte multiples (all of the training step's): 64 x 64
+// tiles, 16-byte global loads and stores on both sides.  Two input rows are packed into one 32-bit word per column, so the
+// transposed tile is written and read as words (pitch 33: the read side is conflict free, the write side two-way).  Each
+// CTA walks a slab of row tiles; with COLSUM it also accumulates the column sums of its slab (the bias gradients) and adds
+// them to colsum_out once -- the separate colsum pass over the same 2.5 GB is gone.
+template <bool IN_BF16, bool COLSUM>
+__global__ void __launch_bounds__(256) transpose16v_kernel(const uint16_t *__restrict__ in, int R, int C, int ld_in,
+                                                           __nv_bfloat16 *__restrict__ out, float *__restrict__ colsum_out) {
+    __shared__ uint32_t tileT[64][33];
+    const int t = threadIdx.x;
+    const int c0 = blockIdx.x * 64;
+    const int tiles = (R + 63) / 64, per = (tiles + gridDim.y - 1) / gridDim.y;
+    const int tile_lo = blockIdx.y * per, tile_hi = min(tiles, tile_lo + per);
+    const int cg = t & 7, rp = t >> 3;                 // load side: 8 columns cg*8.., rows 2*rp and 2*rp + 1
+    const int oc = t >> 2, wq = t & 3;                 // store side: output row (input column) oc, words wq*8 .. wq*8 + 7
+    float csum = 0.0f;
+    auto to_bf16 = [](uint32_t v) -> uint32_t {        // two fp16 -> two bf16
+        if (IN_BF16) return v;
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v));
+        const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+        return *reinterpret_cast<const uint32_t *>(&b);
+    };
+    for (int tile = tile_lo; tile < tile_hi; tile++) {
+        const int r0 = tile * 64;
+        {
+            const int r = r0 + 2 * rp, c = c0 + cg * 8;
+            uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+            if (c < C) {
+                if (r < R) a = *reinterpret_cast<const uint4 *>(in + (size_t)r * ld_in + c);
+                if (r + 1 < R) b = *reinterpret_cast<const uint4 *>(in + (size_t)(r + 1) * ld_in + c);
+            }
+            const uint32_t av[4] = {to_bf16(a.x), to_bf16(a.y), to_bf16(a.z), to_bf16(a.w)};
+            const uint32_t bv[4] = {to_bf16(b.x), to_bf16(b.y), to_bf16(b.z), to_bf16(b.w)};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {              // word (column, row pair) = {row 2rp (low half), row 2rp + 1 (high half)}
+                tileT[cg * 8 + 2 * j][rp] = __byte_perm(av[j], bv[j], 0x5410);
+                tileT[cg * 8 + 2 * j + 1][rp] = __byte_perm(av[j], bv[j], 0x7632);
+            }
+        }
+        __syncthreads();
+        {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = tileT[oc][wq * 8 + k];
+            const int c = c0 + oc, r = r0 + wq * 16;
+            if (c < C) {
+                __nv_bfloat16 *o = out + (size_t)c * R + r;
+                if (r < R) *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (r + 8 < R) *reinterpret_cast<uint4 *>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            if (COLSUM) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {           // rows past R were loaded as zeros
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[k]));
+                    csum += f.x + f.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (COLSUM) {
+        csum += __shfl_xor_sync(0xffffffffu, csum, 1);
+        csum += __shfl_xor_sync(0xffffffffu, csum, 2);
+        if (wq == 0 && c0 + oc < C) atomicAdd(colsum_out + c0 + oc, csum);
+    }
+}
+
+// colsum_out != nullptr: also the column sums of `in` (fp32, zeroed here)
+int transpose_to_bf16(xb_handle *h, const void *in, int R, int C, int ld_in, bool in_bf16, void *out, cudaStream_t s,
+                      float *colsum_out = nullptr) {
+    const uint16_t *src = reinterpret_cast<const uint16_t *>(in);
+    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(out);
+    if (R % 8 == 0 && C % 8 == 0 && ld_in % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int tiles = (R + 63) / 64, ctiles = (C + 63) / 64;
+        int slabs = (148 * 12 + ctiles - 1) / ctiles;         // ~12 CTAs per SM over the whole grid
+        if (slabs > tiles) slabs = tiles;
+        dim3 grid(ctiles, slabs);
+        if (colsum_out) XB_CUDA(h, cudaMemsetAsync(colsum_out, 0, (size_t)C * sizeof(float), s));
+        if (in_bf16 && colsum_out) transpose16v_kernel<true, true><<<grid, 256, 0, s>>>(src, R, C, ld_in, dst, colsum_out);
+        else if (in_bf16) transpose16v_kernel<true, false><<<grid, 256, 0, s>>>(src, R, C, ld_in, dst, nullptr);
+        else if (colsum_out) return xb_fail(h, XB_ERR_ARG, "column sums are taken of bf16 gradients only");
+        else transpose16v_kernel<false, false><<<grid, 256, 0, s>>>(src, R, C, ld_in, dst, nullptr);
+        XB_LAUNCH_CHECK(h);
+        return XB_OK;
+    }
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    if (in_bf16) transpose16_kernel<true><<<grid, block, 0, s>>>(src, R, C, ld_in, dst);
+    else transpose16_kernel<false><<<grid, block, 0, s>>>(src, R, C, ld_in, dst);
+    XB_LAUNCH_CHECK(h);
+    if (colsum_out) return colsum(h, in, R, C, ld_in, colsum_out, s);
     return XB_OK;
 }
 
@@ -379,26 +464,22 @@ int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float 
         const xb_lstm_weights &lw = h->lstm[l];
         const bool reverse = (l % 2) == 0;
         const void *dy = w->dy[(l + 1) & 1];
-        CUtensorMap tmA, tmB;
-        if (int rc = xb_make_tmap_2d(h, &tmA, w->DZ, (uint64_t)TN, XB_GATES, XB_GATES)) return rc;
-        if (int rc = xb_make_tmap_2d(h, &tmB, lw.w_hhT, F, XB_GATES, XB_GATES)) return rc;
+        BpttMaps maps;
+        if (int rc = xb_bptt_make_maps(h, &maps, w->DZ, lw.w_hhT, w->saved[l], T, N)) return rc;
         for (int i = 0; i < T; i++) {                       // forward ran t = (reverse ? T-1 .. 0 : 0 .. T-1); walk it backwards
             const int t = reverse ? i : T - 1 - i;
             const int t_next = reverse ? t - 1 : t + 1;     // the step the forward ran AFTER t (its dz feeds dh_t); i == 0: none
             const int t_prev = reverse ? t + 1 : t - 1;     // the step the forward ran BEFORE t (its c is c_prev)
-            GemmParams p;
-            p.M = N; p.N = F; p.K = XB_GATES; p.NB = N;
-            p.a_row_offset = (i == 0) ? 0 : t_next * N;
-            p.first = (i == 0);
-            p.t_cur = t;
+            BpttStep p;
+            p.N = N; p.t_cur = t;
+            p.t_next = (i == 0) ? -1 : t_next;
             p.t_prev = (t_prev >= 0 && t_prev < T) ? t_prev : -1;
-            p.saved = w->saved[l]; p.dy = dy; p.dz = w->DZ; p.dcstate = w->dcstate;
-            if (int rc = xb_gemm_launch(h, EPI_LSTM_BWD, tmA, tmB, p, s, true)) return rc;
+            p.dy = dy; p.dcstate = w->dcstate;
+            if (int rc = xb_bptt_step_launch(h, maps, p, /*dependent=*/i > 0, s)) return rc;
         }
         float *g_wih = grads[6 + 4 * l], *g_whh = grads[7 + 4 * l], *g_bih = grads[8 + 4 * l], *g_bhh = grads[9 + 4 * l];
-        if (int rc = colsum(h, w->DZ, TN, XB_GATES, XB_GATES, g_bih, s)) return rc;
+        if (int rc = transpose_to_bf16(h, w->DZ, TN, XB_GATES, XB_GATES, true, w->DZT, s, g_bih)) return rc;   // + db = colsum DZ
         XB_CUDA(h, cudaMemcpyAsync(g_bhh, g_bih, XB_GATES * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (int rc = transpose_to_bf16(h, w->DZ, TN, XB_GATES, XB_GATES, true, w->DZT, s)) return rc;
         if (int rc = transpose_to_bf16(h, w->x[l], TN, F, F, false, w->XT[l & 1], s)) return rc;
         if (int rc = gemm_bf16(h, EPI_F32, w->DZT, XB_GATES, TN, w->XT[l & 1], F, TN, TN, g_wih, F, s)) return rc;
         // dW_hh = sum over the steps that had a predecessor of dz_t (x) h_prev: a time shift of N columns between DZ^T and Y^T
@@ -425,8 +506,7 @@ int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float 
         GemmParams p;
         p.M = TN; p.N = F; p.K = XB_CONV3_K; p.bias = h->conv3_b; p.out = w->dpre; p.ldo = F; p.T = T; p.NB = N; p.dy = w->dy[0];
         if (int rc = xb_gemm_launch(h, EPI_CONV3_BWD, tmA, tmB, p, s, false)) return rc;
-        if (int rc = colsum(h, w->dpre, TN, F, F, grads[5], s)) return rc;
-        if (int rc = transpose_to_bf16(h, w->dpre, TN, F, F, true, w->dpreT, s)) return rc;
+        if (int rc = transpose_to_bf16(h, w->dpre, TN, F, F, true, w->dpreT, s, grads[5])) return rc;       // + db3 = colsum d pre
         if (int rc = transpose_to_bf16(h, h->c2, TN, XB_CONV3_K, XB_CONV3_K, false, w->colT, s)) return rc;
         // dW3 in im2col column order (768, 320): the caller drops the 16 padding columns and permutes to (768, 16, 19)
         if (int rc = gemm_bf16(h, EPI_F32, w->dpreT, F, TN, w->colT, XB_CONV3_K, TN, TN, grads[4], XB_CONV3_K, s)) return rc;

@@ -31,5 +31,23 @@ int xb_make_tmap_2d_box(xb_handle *h, CUtensorMap *out, const void *base, uint64
                         uint32_t box_inner, uint32_t box_rows, int swizzle128);
 int xb_make_tmap_hview(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint32_t box_rows,
                        uint32_t box_kblocks);
+int xb_make_tmap_nd(xb_handle *h, CUtensorMap *out, const void *base, int rank, int elem_bytes, const uint64_t *dims,
+                    const uint64_t *strides_bytes, const uint32_t *box);
+
+// lstm_bptt.cu: one step of back-propagation through time of an LSTM layer (programmatic dependent launches)
+struct BpttMaps {
+    CUtensorMap dz_rows;           // DZ as (T*N, 3072) bf16: the A operand dz_{t_next}
+    CUtensorMap w_hhT;             // W_hh^T (768, 3072) bf16, 64-row boxes
+    CUtensorMap saved;             // saved (768, N, 5, T) fp16 view, box {64, 128, 5, 1}
+    CUtensorMap saved_c;           // same tensor, box {64, 128, 1, 1}: the cell state of the previous step
+    CUtensorMap dz_out;            // DZ as (768, N, 4, T) bf16 view, box {64, 128, 4, 1}
+};
+struct BpttStep {
+    int N = 0, t_cur = 0, t_prev = -1, t_next = -1;      // t_next < 0: first BPTT step of the layer (no recurrent term)
+    const void *dy = nullptr;      // (T, N, 768) bf16
+    float *dcstate = nullptr;      // (N, 768) fp32
+};
+int xb_bptt_make_maps(xb_handle *h, BpttMaps *m, const void *dz, const void *w_hhT, const void *saved, int T, int N);
+int xb_bptt_step_launch(xb_handle *h, const BpttMaps &m, const BpttStep &p, bool dependent, cudaStream_t s);
 int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p,
                    cudaStream_t s, bool bf16_operands = false);
