@@ -248,10 +248,12 @@ int64_t xb_launch_count(const xb_handle *h);
 
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline numbers).
  * Stages: 0 conv1+conv2+im2col, 1 conv3 GEMM, 2 LSTM input-projection GEMMs, 3 LSTM recurrence,
- * 4 CRF head GEMM, 5 CRF alpha sweep, 6 CRF backward sweep, 7 CRF Viterbi sweep + packing.
+ * 4 CRF head GEMM, 5 CRF alpha sweep, 6 CRF backward sweep, 7 CRF Viterbi sweep + packing;
+ * of xb_encoder_bwd: 8 BPTT step kernels, 9 transposed copies (+ bias gradients), 10 weight-gradient GEMMs (K = T*N),
+ * 11 input-gradient GEMMs, 12 head and convolution-stem backward kernels.
  * xb_stage_times synchronises, adds the elapsed milliseconds and launch-span counts of every span
  * recorded since the last call into ms[XB_NUM_STAGES] / spans[XB_NUM_STAGES], and clears them. */
-#define XB_NUM_STAGES 8
+#define XB_NUM_STAGES 13
 int xb_set_profiling(xb_handle *h, int on);
 int xb_stage_times(xb_handle *h, float *ms, int *spans);
 

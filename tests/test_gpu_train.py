@@ -35,7 +35,8 @@ def _compare(got, ref, skip=()):
     return worst
 
 
-@pytest.mark.parametrize('n_base,N,L', [(5, 8, 500), (6, 16, 300)])
+# N = 136: two row tiles of the BPTT step kernel, the second clipped at the batch edge by its tensor maps
+@pytest.mark.parametrize('n_base,N,L', [(5, 8, 500), (6, 16, 300), (5, 136, 100)])
 def test_encoder_backward_matches_autograd(n_base, N, L):
     from xna_basecaller_b200._lib import Handle
     sd = bo.reference_state_dict(n_base=n_base, seed=12, **REF_SCALE)

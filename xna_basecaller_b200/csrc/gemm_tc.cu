@@ -27,10 +27,10 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 // Pipeline depth.  Three stages (96 KB) leave room for two CTAs per SM, whose epilogues and main loops overlap.  The
-// one-launch-per-step recurrence GEMMs (a 24-tile grid with K = 3072: one CTA per SM, latency-bound on the TMA round trip)
-// run six stages instead: 192 KB in flight per SM.
+// one-launch-per-step recurrence GEMM of the cross-check builds (a 24-tile grid: one CTA per SM, latency-bound on the TMA
+// round trip) runs six stages instead: 192 KB in flight per SM.
 template <int EPI> struct Pipe {
-    static constexpr int STAGES = (EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) ? 6 : 3;
+    static constexpr int STAGES = (EPI == EPI_LSTM) ? 6 : 3;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -43,7 +43,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 
 template <bool BF16, int EPI>
-__global__ void __launch_bounds__(256, (EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) ? 1 : 2)
+__global__ void __launch_bounds__(256, (EPI == EPI_LSTM) ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int STAGES = Pipe<EPI>::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -56,7 +56,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     // K need not be a multiple of 64: the tensor maps are built over exactly K columns and TMA zero-fills the rest
-    const int kblocks = ((EPI == EPI_LSTM || EPI == EPI_LSTM_BWD) && p.first) ? 0 : (p.K + BK - 1) / BK;
+    const int kblocks = (EPI == EPI_LSTM && p.first) ? 0 : (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -116,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // warps; every other epilogue runs on all eight warps (the producer / MMA warps are idle once the main loop has
     // been issued): warps 0-3 take tile columns 0..63, warps 4-7 columns 64..127.  (EPI_F32, the self test, also keeps four.)
     __syncwarp();
-    if ((EPI == EPI_LSTM || EPI == EPI_F32 || EPI == EPI_LSTM_BWD || EPI == EPI_BF16OUT || EPI == EPI_CONV3_BWD) ? warp >= 4 : true) {
+    if ((EPI == EPI_LSTM || EPI == EPI_F32 || EPI == EPI_BF16OUT || EPI == EPI_CONV3_BWD) ? warp >= 4 : true) {
         const int q = warp & 3;
         const int r = q * 32 + lane;             // tile row == TMEM lane
         const int m = m0 + r;
@@ -184,87 +184,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     hv.x = X::pack(hn[0], hn[1]); hv.y = X::pack(hn[2], hn[3]);
                     hv.z = X::pack(hn[4], hn[5]); hv.w = X::pack(hn[6], hn[7]);
                     *reinterpret_cast<uint4 *>(hout + ub) = hv;
-                }
-            }
-        } else if constexpr (EPI == EPI_LSTM_BWD) {
-            // One BPTT step of an LSTM layer (the backward of nn.py:189-193's torch.nn.LSTM): row = chunk, columns = 128
-            // hidden units.  acc = dz_{next} W_hh = the recurrent part of dL/dh_t; dy[t] the part from the layer above.
-            //   dc = dh o (1 - tanh^2 c) + dc_next;   do = dh tanh c;  di = dc g;  dg = dc i;  df = dc c_prev;  dc_prev = dc f
-            //   dz = (di i(1-i), df f(1-f), dg (1-g^2), do o(1-o))  -> DZ[t] in the reference's gate-row order
-            const int u0 = n0;
-            const size_t cell = (size_t)p.t_cur * p.NB + m;
-            const __half *sv = reinterpret_cast<const __half *>(p.saved) + cell * 5 * XB_FEATURES + u0;
-            const __half *cp = p.t_prev >= 0 ? reinterpret_cast<const __half *>(p.saved) +
-                                                   (((size_t)p.t_prev * p.NB + m) * 5 + 4) * XB_FEATURES + u0 : nullptr;
-            const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16 *>(p.dy) + cell * XB_FEATURES + u0;
-            __nv_bfloat16 *dzp = reinterpret_cast<__nv_bfloat16 *>(p.dz) + cell * XB_GATES + u0;
-            float *dcs = p.dcstate + (size_t)m * XB_FEATURES + u0;
-#pragma unroll 2
-            for (int ub = 0; ub < BN; ub += 8) {
-                uint32_t acc[8];
-                if (kblocks > 0) {
-                    tmem_ld_32x32b_x8(taddr + ub, acc);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) acc[j] = 0u;
-                }
-                if (row_ok) {
-                    auto ld8h = [](const __half *q, float (&o)[8]) {
-                        const uint4 raw = *reinterpret_cast<const uint4 *>(q);
-                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) { float2 f = __half22float2(h2[j]); o[2 * j] = f.x; o[2 * j + 1] = f.y; }
-                    };
-                    float gi[8], gf[8], gg[8], go[8], cc[8], cprev[8], dyv[8], dcin[8];
-                    ld8h(sv + 0 * XB_FEATURES + ub, gi);
-                    ld8h(sv + 1 * XB_FEATURES + ub, gf);
-                    ld8h(sv + 2 * XB_FEATURES + ub, gg);
-                    ld8h(sv + 3 * XB_FEATURES + ub, go);
-                    ld8h(sv + 4 * XB_FEATURES + ub, cc);
-                    if (cp) ld8h(cp + ub, cprev);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) cprev[j] = 0.0f;
-                    }
-                    {
-                        const uint4 raw = *reinterpret_cast<const uint4 *>(dyp + ub);
-                        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) { float2 f = __bfloat1622float2(b2[j]); dyv[2 * j] = f.x; dyv[2 * j + 1] = f.y; }
-                    }
-                    if (p.first) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) dcin[j] = 0.0f;
-                    } else {
-                        const float4 a = *reinterpret_cast<const float4 *>(dcs + ub), b = *reinterpret_cast<const float4 *>(dcs + ub + 4);
-                        dcin[0] = a.x; dcin[1] = a.y; dcin[2] = a.z; dcin[3] = a.w; dcin[4] = b.x; dcin[5] = b.y; dcin[6] = b.z; dcin[7] = b.w;
-                    }
-                    float dzi[8], dzf[8], dzg[8], dzo[8], dcp[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float dh = __uint_as_float(acc[j]) + dyv[j];
-                        const float tc = tanhf(cc[j]);
-                        const float dc = dh * go[j] * (1.0f - tc * tc) + dcin[j];
-                        dzo[j] = dh * tc * go[j] * (1.0f - go[j]);
-                        dzi[j] = dc * gg[j] * gi[j] * (1.0f - gi[j]);
-                        dzg[j] = dc * gi[j] * (1.0f - gg[j] * gg[j]);
-                        dzf[j] = dc * cprev[j] * gf[j] * (1.0f - gf[j]);
-                        dcp[j] = dc * gf[j];
-                    }
-                    auto st8b = [](__nv_bfloat16 *q, const float (&v)[8]) {
-                        uint4 raw;
-                        __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&raw);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) b2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(q) = raw;
-                    };
-                    st8b(dzp + 0 * XB_FEATURES + ub, dzi);
-                    st8b(dzp + 1 * XB_FEATURES + ub, dzf);
-                    st8b(dzp + 2 * XB_FEATURES + ub, dzg);
-                    st8b(dzp + 3 * XB_FEATURES + ub, dzo);
-                    *reinterpret_cast<float4 *>(dcs + ub) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
-                    *reinterpret_cast<float4 *>(dcs + ub + 4) = make_float4(dcp[4], dcp[5], dcp[6], dcp[7]);
                 }
             }
         } else if constexpr (EPI == EPI_BF16OUT) {
@@ -513,7 +432,6 @@ int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensor
         switch (epi) {
             case EPI_F32: return launch_one<true, EPI_F32>(h, tmA, tmB, p, p.M, s);
             case EPI_BF16OUT: return launch_one<true, EPI_BF16OUT>(h, tmA, tmB, p, p.M, s);
-            case EPI_LSTM_BWD: return launch_one<true, EPI_LSTM_BWD>(h, tmA, tmB, p, p.M, s);
         }
         return xb_fail(h, XB_ERR_ARG, "no bf16 GEMM with epilogue %d", epi);
     }

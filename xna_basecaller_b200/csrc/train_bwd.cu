@@ -14,15 +14,16 @@
 // reference needs a GradScaler for the same reason), products accumulate in fp32 on the tensor cores, weight gradients
 // are written in fp32.
 //   head     dz = dS[non-blank] * scale * (1 - tanh^2) from the stored scores;  dW = dz^T x5;  db = colsum dz;  dy5 = dz W
-//   LSTM l   T launches of the tile GEMM with the EPI_LSTM_BWD epilogue, one per time step in reverse forward order:
-//            dh_t = dz_{next} W_hh + dy_t, then the cell backward in the epilogue -> DZ[t] (T*N, 3072) and the running dc;
-//            dW_ih = DZ^T x_l,  dW_hh = DZ^T h_prev (time-shifted view of the layer output),  db = colsum DZ,
-//            dy_{l-1} = DZ W_ih.   The K = T*N contractions run on K-major transposed copies (transpose16_kernel).
+//   LSTM l   T launches of the BPTT step kernel (lstm_bptt.cu), one per time step in reverse forward order, chained with
+//            programmatic dependent launches: dh_t = dz_{next} W_hh + dy_t, then the cell backward -> DZ[t] (T*N, 3072)
+//            and the running dc;  dW_ih = DZ^T x_l,  dW_hh = DZ^T h_prev (time-shifted view of the layer output),
+//            db = colsum DZ (taken inside the transposition),  dy_{l-1} = DZ W_ih.   The K = T*N contractions run on
+//            K-major transposed copies (transpose16v_kernel).
 //   conv3    pre-activation recomputed from the im2col rows (EPI_CONV3_BWD) -> d pre;  dW3 = d pre^T col;  db3;
 //            d col = d pre W3 -> col2im -> conv2 / conv1 backward (conv_stem_bwd kernels below).
-// The per-step launches make the recurrence launch-bound (~10 us per step against ~3.6 us in the persistent forward
-// kernel); a persistent backward kernel (W_hh^T needs 786 KB per 128 hidden units, i.e. a K-split with a cross-SM
-// reduction every step) is the known next step and is discussed in DESIGN.md.
+// Measured at N = 512, T = 800 (profiles/r02_config5_train_step_v4.json): 165 ms per training step, of which the 4000 BPTT
+// steps take ~70 ms (17.6 us each: ~10 us of main loop bound by one SM's L2 ingest of its 1.15 MB of operands, the rest
+// epilogue and the kernel hand-over), the K = T*N weight-gradient GEMMs ~28 ms and the forward ~25 ms.
 #include "xb_common.cuh"
 #include "xb_gemm.cuh"
 
@@ -336,6 +337,7 @@ int transpose_to_bf16(xb_handle *h, const void *in, int R, int C, int ld_in, boo
                       float *colsum_out = nullptr) {
     const uint16_t *src = reinterpret_cast<const uint16_t *>(in);
     __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(out);
+    xb_stage_timer tm(h, XB_ST_TRAIN_TRANSPOSE, s);
     if (R % 8 == 0 && C % 8 == 0 && ld_in % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int tiles = (R + 63) / 64, ctiles = (C + 63) / 64;
         int slabs = (148 * 12 + ctiles - 1) / ctiles;         // ~12 CTAs per SM over the whole grid
@@ -365,6 +367,7 @@ int gemm_bf16(xb_handle *h, int epi, const void *A, int M, int lda, const void *
     if (int rc = xb_make_tmap_2d(h, &tmB, B, (uint64_t)Nn, (uint64_t)K, (uint64_t)ldb)) return rc;
     GemmParams p;
     p.M = M; p.N = Nn; p.K = K; p.out = out; p.ldo = ldo;
+    xb_stage_timer tm(h, epi == EPI_F32 ? XB_ST_TRAIN_WGRAD : XB_ST_TRAIN_XGRAD, s);
     return xb_gemm_launch(h, epi, tmA, tmB, p, s, true);
 }
 
@@ -466,6 +469,8 @@ int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float 
         const void *dy = w->dy[(l + 1) & 1];
         BpttMaps maps;
         if (int rc = xb_bptt_make_maps(h, &maps, w->DZ, lw.w_hhT, w->saved[l], T, N)) return rc;
+        {
+        xb_stage_timer tm_bptt(h, XB_ST_TRAIN_BPTT, s);
         for (int i = 0; i < T; i++) {                       // forward ran t = (reverse ? T-1 .. 0 : 0 .. T-1); walk it backwards
             const int t = reverse ? i : T - 1 - i;
             const int t_next = reverse ? t - 1 : t + 1;     // the step the forward ran AFTER t (its dz feeds dh_t); i == 0: none
@@ -476,6 +481,7 @@ int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float 
             p.t_prev = (t_prev >= 0 && t_prev < T) ? t_prev : -1;
             p.dy = dy; p.dcstate = w->dcstate;
             if (int rc = xb_bptt_step_launch(h, maps, p, /*dependent=*/i > 0, s)) return rc;
+        }
         }
         float *g_wih = grads[6 + 4 * l], *g_whh = grads[7 + 4 * l], *g_bih = grads[8 + 4 * l], *g_bhh = grads[9 + 4 * l];
         if (int rc = transpose_to_bf16(h, w->DZ, TN, XB_GATES, XB_GATES, true, w->DZT, s, g_bih)) return rc;   // + db = colsum DZ

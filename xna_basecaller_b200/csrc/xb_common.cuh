@@ -29,7 +29,8 @@ struct xb_lstm_weights {
 };
 
 enum { XB_ST_CONV12 = 0, XB_ST_CONV3, XB_ST_INPROJ, XB_ST_LSTM_REC, XB_ST_HEAD, XB_ST_CRF_ALPHA, XB_ST_CRF_BACKWARD,
-       XB_ST_CRF_VITERBI, XB_ST_COUNT };
+       XB_ST_CRF_VITERBI, XB_ST_TRAIN_BPTT, XB_ST_TRAIN_TRANSPOSE, XB_ST_TRAIN_WGRAD, XB_ST_TRAIN_XGRAD, XB_ST_TRAIN_HEAD_CONV,
+       XB_ST_COUNT };
 
 struct xb_prof_span { int stage; cudaEvent_t a, b; };
 

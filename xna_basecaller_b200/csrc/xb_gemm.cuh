@@ -2,7 +2,7 @@
 #pragma once
 #include "xb_common.cuh"
 
-enum { EPI_F32 = 0, EPI_CONV3 = 1, EPI_INPROJ = 2, EPI_HEAD = 3, EPI_LSTM = 4, EPI_BF16OUT = 5, EPI_LSTM_BWD = 6, EPI_CONV3_BWD = 7 };
+enum { EPI_F32 = 0, EPI_CONV3 = 1, EPI_INPROJ = 2, EPI_HEAD = 3, EPI_LSTM = 4, EPI_BF16OUT = 5, EPI_CONV3_BWD = 7 };
 
 struct GemmParams {
     int M = 0, N = 0, K = 0;       // logical problem (rows of A that are valid, columns = rows of B, depth)
@@ -18,12 +18,8 @@ struct GemmParams {
     const void *gates = nullptr;   // (T, NB, 3072) 16-bit input projection (+bias)
     float *cstate = nullptr;       // (NB, 768) fp32
     int t_cur = 0, first = 0;
-    // training backward (EPI_LSTM_BWD: one BPTT step; EPI_CONV3_BWD: recomputed conv3 pre-activation -> its gradient)
-    const void *saved = nullptr;   // (T, NB, 5, 768) fp16: i, f, g, o (activated) and c of the forward pass
-    const void *dy = nullptr;      // (T, NB, 768) bf16: gradient w.r.t. the layer output (conv3: w.r.t. the stem output)
-    void *dz = nullptr;            // (T, NB, 3072) bf16: gradient w.r.t. the gate pre-activations, reference row order
-    float *dcstate = nullptr;      // (NB, 768) fp32: gradient w.r.t. the cell state carried between steps
-    int t_prev = -1;               // the step the forward pass ran before t_cur (-1: t_cur was its first step)
+    // training backward (EPI_CONV3_BWD: recomputed conv3 pre-activation -> its gradient)
+    const void *dy = nullptr;      // (T, NB, 768) bf16: gradient w.r.t. the stem output
 };
 
 int xb_make_tmap_2d(xb_handle *h, CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint64_t ld);
