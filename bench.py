@@ -314,16 +314,21 @@ def run_readset(args, rank, world, local):
     barrier()
     t0 = time.perf_counter()
     e2e_reads = 0
+    phase = {'seconds_stage_h2d': 0.0, 'seconds_gpu_batches': 0.0, 'seconds_strings': 0.0}
     for step in range(args.steps):
         queue = pipeline.WorkQueue(n_blocks, store=store, key='xb_readset_pass_%d' % step)
         for strings, c in caller.basecall_stream(block(k) for k in queue):
             e2e_reads += c['reads']
+            for k_ in phase:
+                phase[k_] += c[k_]
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.summary()
 
     table = pipeline.gather_counters({'dev_ms': dev_ms, 'e2e_ms': e2e_s * 1e3, 'samples': my_samples, 'chunks': chunks,
-                                      'bases': bases, 'e2e_reads': e2e_reads, 'launches': launches},
+                                      'bases': bases, 'e2e_reads': e2e_reads, 'launches': launches,
+                                      'stage_s': phase['seconds_stage_h2d'], 'gpu_s': phase['seconds_gpu_batches'],
+                                      'strings_s': phase['seconds_strings']},
                                      device=dev if world > 1 else None)
     if rank == 0:
         total = float(lengths.sum())
@@ -347,6 +352,11 @@ def run_readset(args, rank, world, local):
                     'h2d_bytes_per_step': int(total * 4), 'd2h_bytes_per_step': int(sum(table['bases']) / args.steps)},
             'gpu_launches': int(sum(table['launches'])),
             'mean_decoded_len_per_read': sum(table['bases']) / args.steps / n_reads,
+            # e2e pass, per rank (seconds summed over its blocks; the phases of consecutive blocks overlap): host staging + H2D
+            # issue, kernel launches + wait for the letters, string cutting -- against the rank's wall time
+            'e2e_phase_seconds_per_rank': {'stage_h2d': table['stage_s'], 'launch_and_wait': table['gpu_s'],
+                                           'strings': table['strings_s'], 'wall': [v / 1e3 for v in table['e2e_ms']],
+                                           'device_pass': [v / 1e3 for v in table['dev_ms']], 'host_cpus': os.cpu_count()},
             'clocks': clocks,
         }
         print(json.dumps(line))

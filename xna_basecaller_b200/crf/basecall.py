@@ -33,6 +33,8 @@ def compute_scores(model, batch, beam_width=32, beam_cut=100.0, scale=1.0, offse
     """Compute scores for model: batch (N, 1, chunksize) host tensor -> {'sequence', 'qstring', 'moves'}."""
     head = model.encoder[-1]
     device = next(model.parameters()).device
+    if device.type == 'cuda':
+        torch.cuda.set_device(device)       # basecall() runs this on a pipeline thread; the current device is per-thread state
     N, _, L = batch.shape
     T = L // model.stride
     if not head.expand_blanks:
@@ -82,6 +84,8 @@ def _submit_scores(model, batch, slot):
     if not model.encoder[-1].expand_blanks or model.encoder._stem() is None:
         raise RuntimeError('the pipelined path needs the sup@v3.3 encoder layout with expand_blanks')
     device = next(model.parameters()).device
+    if device.type == 'cuda':
+        torch.cuda.set_device(device)
     N, _, L = batch.shape
     T = L // model.stride
     h = model.seqdist.engine.get(device, N, T, bf16=next(model.parameters()).dtype == torch.bfloat16)
