@@ -56,7 +56,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     // K need not be a multiple of 64: the tensor maps are built over exactly K columns and TMA zero-fills the rest
-    const int kblocks = (EPI == EPI_LSTM && p.first) ? 0 : (p.K + BK - 1) / BK;
+    // split-K (EPI_F32 only, gridDim.z slices): slice z covers K blocks [kb0, kb0 + kblocks) and adds its partial tile to the
+    // zeroed output -- for the weight-gradient contractions whose output has fewer tiles than the GPU has SMs
+    const int kb_all = (p.K + BK - 1) / BK;
+    const int kb_per = (kb_all + gridDim.z - 1) / gridDim.z;
+    const int kb0 = blockIdx.z * kb_per;
+    const int kblocks = (EPI == EPI_LSTM && p.first) ? 0 : max(0, min(kb_all, kb0 + kb_per) - kb0);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -87,8 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 uint8_t *sa = smem + s * STAGE_BYTES;
-                tma_load_2d(sa, &tmA, &full[s], kb * BK, m0 + p.a_row_offset);
-                tma_load_2d(sa + TILE_A_BYTES, &tmB, &full[s], kb * BK, n0);
+                tma_load_2d(sa, &tmA, &full[s], (kb0 + kb) * BK, m0 + p.a_row_offset);
+                tma_load_2d(sa + TILE_A_BYTES, &tmB, &full[s], (kb0 + kb) * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -236,16 +241,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         } else if constexpr (EPI == EPI_F32) {
 #pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
+            for (int cb = 0; cb < (kblocks > 0 ? BN : 0); cb += 32) {       // an empty K slice contributes nothing
                 uint32_t acc[32];
                 tmem_ld_32x32b_x32(taddr + cb, acc);
                 tmem_ld_wait();
                 const int nb = n0 + cb;
                 if (row_ok) {
                     float *o = reinterpret_cast<float *>(p.out) + (size_t)m * p.ldo + nb;
+                    if (gridDim.z > 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (nb + j < p.N) o[j] = __uint_as_float(acc[j]);
+                        for (int j = 0; j < 32; j++)
+                            if (nb + j < p.N) atomicAdd(o + j, __uint_as_float(acc[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (nb + j < p.N) o[j] = __uint_as_float(acc[j]);
+                    }
                 }
             }
         } else {
@@ -419,7 +430,7 @@ static int launch_one(xb_handle *h, const CUtensorMap &tmA, const CUtensorMap &t
         XB_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured[h->device & 63] = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (rows_a + BM - 1) / BM);
+    dim3 grid((p.N + BN - 1) / BN, (rows_a + BM - 1) / BM, (EPI == EPI_F32 && p.split_k > 1) ? p.split_k : 1);
     k<<<grid, 256, SMEM_BYTES, s>>>(tmA, tmB, p);
     XB_LAUNCH_CHECK(h);
     return XB_OK;

@@ -21,14 +21,16 @@
 //            K-major transposed copies (transpose16v_kernel).
 //   conv3    pre-activation recomputed from the im2col rows (EPI_CONV3_BWD) -> d pre;  dW3 = d pre^T col;  db3;
 //            d col = d pre W3 -> col2im -> conv2 / conv1 backward (conv_stem_bwd kernels below).
-// Measured at N = 512, T = 800 (profiles/r02_config5_train_step_v4.json): 165 ms per training step, of which the 4000 BPTT
-// steps take ~70 ms (17.6 us each: ~10 us of main loop bound by one SM's L2 ingest of its 1.15 MB of operands, the rest
-// epilogue and the kernel hand-over), the K = T*N weight-gradient GEMMs ~28 ms and the forward ~25 ms.
+// Measured at N = 512, T = 800 (profiles/r02_config5_train_step_v5.json): 154 ms per training step, of which the 4000 BPTT
+// steps take ~69 ms (17.3 us each: ~10 us of main loop bound by one SM's L2 ingest of its 1.15 MB of operands, the rest
+// epilogue and the kernel hand-over), the K = T*N weight-gradient GEMMs ~20 ms (wgrad_gemm.cu) and the forward ~25 ms.
 #include "xb_common.cuh"
 #include "xb_gemm.cuh"
 
 int xb_conv12_im2col(xb_handle *h, const void *signal, int sig_dtype, int N, int L, cudaStream_t s);
 int xb_lstm_recurrence_persistent(xb_handle *h, int layer, void *y_tnc, int T, int N, int reverse, cudaStream_t s, void *save);
+int xb_lstm_wgrad_launch(xb_handle *h, const void *dzT, const void *xT, const void *yT, int T, int N, bool reverse, float *g_wih,
+                         float *g_whh, cudaStream_t s);
 int xb_inproj_launch(xb_handle *h, const void *x, const void *w_ih, const float *bias, void *gates, int M, cudaStream_t s);
 
 struct xb_train_ws {
@@ -368,6 +370,16 @@ int gemm_bf16(xb_handle *h, int epi, const void *A, int M, int lda, const void *
     GemmParams p;
     p.M = M; p.N = Nn; p.K = K; p.out = out; p.ldo = ldo;
     xb_stage_timer tm(h, epi == EPI_F32 ? XB_ST_TRAIN_WGRAD : XB_ST_TRAIN_XGRAD, s);
+    if (epi == EPI_F32) {
+        // weight gradients: few output tiles, K = T*N deep -- slice K until the grid covers the SMs (partials added in L2)
+        const int tiles = ((M + 127) / 128) * ((Nn + 127) / 128), kb = (K + 63) / 64;
+        int split = tiles >= 148 ? 1 : (2 * 148) / tiles;
+        if (split > kb / 8) split = kb / 8 > 0 ? kb / 8 : 1;
+        if (split > 1) {
+            p.split_k = split;
+            XB_CUDA(h, cudaMemsetAsync(out, 0, (size_t)M * ldo * sizeof(float), s));
+        }
+    }
     return xb_gemm_launch(h, epi, tmA, tmB, p, s, true);
 }
 
@@ -487,19 +499,11 @@ int xb_encoder_bwd(xb_handle *h, const void *signal, int sig_dtype, const float 
         if (int rc = transpose_to_bf16(h, w->DZ, TN, XB_GATES, XB_GATES, true, w->DZT, s, g_bih)) return rc;   // + db = colsum DZ
         XB_CUDA(h, cudaMemcpyAsync(g_bhh, g_bih, XB_GATES * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (int rc = transpose_to_bf16(h, w->x[l], TN, F, F, false, w->XT[l & 1], s)) return rc;
-        if (int rc = gemm_bf16(h, EPI_F32, w->DZT, XB_GATES, TN, w->XT[l & 1], F, TN, TN, g_wih, F, s)) return rc;
-        // dW_hh = sum over the steps that had a predecessor of dz_t (x) h_prev: a time shift of N columns between DZ^T and Y^T
+        // dW_ih = DZ^T x_l and dW_hh = sum over the steps that had a predecessor of dz_t (x) h_prev (a time shift of N columns
+        // between DZ^T and Y^T), one launch over 128 x 256 tiles (wgrad_gemm.cu)
         {
-            const char *dzt = reinterpret_cast<const char *>(w->DZT), *yt = reinterpret_cast<const char *>(w->XT[(l + 1) & 1]);
-            const size_t shift = (size_t)N * 2;               // bytes of one time step along a transposed row
-            const int K = TN - N;
-            if (K > 0) {
-                const void *A = reverse ? dzt : dzt + shift;  // reverse: steps t = 0 .. T-2 pair with h at t+1
-                const void *B = reverse ? yt + shift : yt;    // forward: steps t = 1 .. T-1 pair with h at t-1
-                if (int rc = gemm_bf16(h, EPI_F32, A, XB_GATES, TN, B, F, TN, K, g_whh, F, s)) return rc;
-            } else {
-                XB_CUDA(h, cudaMemsetAsync(g_whh, 0, (size_t)XB_GATES * F * sizeof(float), s));
-            }
+            xb_stage_timer tm(h, XB_ST_TRAIN_WGRAD, s);
+            if (int rc = xb_lstm_wgrad_launch(h, w->DZT, w->XT[l & 1], w->XT[(l + 1) & 1], T, N, reverse, g_wih, g_whh, s)) return rc;
         }
         if (int rc = gemm_bf16(h, EPI_BF16OUT, w->DZ, TN, XB_GATES, lw.w_ihT, F, XB_GATES, XB_GATES, w->dy[l & 1], F, s)) return rc;
     }

@@ -7,6 +7,7 @@ enum { EPI_F32 = 0, EPI_CONV3 = 1, EPI_INPROJ = 2, EPI_HEAD = 3, EPI_LSTM = 4, E
 struct GemmParams {
     int M = 0, N = 0, K = 0;       // logical problem (rows of A that are valid, columns = rows of B, depth)
     int a_row_offset = 0;          // added to the A row coordinate (LSTM: row block of h_{t-1})
+    int split_k = 1;               // EPI_F32: K slices (gridDim.z) whose partial tiles are ADDED to a zeroed output
     const float *bias = nullptr;   // (N) fp32
     void *out = nullptr;
     int ldo = 0;                   // output row pitch in elements
