@@ -80,6 +80,45 @@ out = {'config': 'configs[4]: training step fwd_bwd, batch %d x 4000 samples, ta
 for name, fn, reps in (('fwd_loss', fwd_loss, 5), ('fwd_loss_bwd_to_all_parameters', fwd_bwd, 3), ('train_one_step', full_step, 3)):
     ms, val = timed(fn, reps)
     out[name] = {'ms_per_step': ms, 'samples_per_s': N * 4000 / ms * 1e3, 'loss': float(val)}
+
+
+# The reference's PyTorch path on THIS GPU for the same step, as far as it can be restated without the seqdist wheel: the module
+# graph through torch autograd under fp16 autocast (cuDNN LSTM forward + backward, cuBLAS, cuDNN convolutions), fp32 master
+# weights, a fixed cotangent on the scores in place of the loss backward.  Encoder only: a LOWER bound on the reference's step.
+def torch_encoder_fwd_bwd():
+    sd = model.state_dict()
+    params = {k: v.detach().clone().cuda().requires_grad_() for k, v in sd.items() if k.startswith('encoder.')}
+    lstms = []
+    for layer in range(4, 9):
+        m = torch.nn.LSTM(768, 768).cuda()
+        with torch.no_grad():
+            for name in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0'):
+                getattr(m, name).copy_(sd['encoder.%d.rnn.%s' % (layer, name)])
+        m.flatten_parameters()
+        lstms.append(m)
+    cot = torch.randn(800, N, 750, generator=torch.Generator().manual_seed(2)).cuda() * 1e-3
+
+    def step():
+        for p_ in list(params.values()) + [q for m in lstms for q in m.parameters()]:
+            p_.grad = None
+        with torch.autocast('cuda', dtype=torch.float16):
+            y = bo.conv_stem(params, x).permute(2, 0, 1).contiguous()
+            for m, rev in zip(lstms, bo.LSTM_DIRECTIONS):
+                y = m(y.flip(0))[0].flip(0) if rev else m(y)[0]
+            scores = bo.crf_head(params, y, 5)
+        scores.float().backward(cot)
+        return scores.detach().float().mean()
+    return timed(step, 3)
+
+
+try:
+    ms, _ = torch_encoder_fwd_bwd()
+    out['torch_cudnn_encoder_fwd_bwd_same_gpu'] = {'ms_per_step': ms, 'samples_per_s': N * 4000 / ms * 1e3,
+                                                   'what': 'torch %s autograd, fp16 autocast, cuDNN LSTM: encoder forward + '
+                                                           'backward only (no loss, no optimiser)' % torch.__version__}
+except Exception as e:                                   # comparator only: never fail the measurement of the product
+    out['torch_cudnn_encoder_fwd_bwd_same_gpu'] = {'error': repr(e)[:200]}
+torch.cuda.empty_cache()
 h = model.seqdist.engine.handle
 h.set_profiling(True)
 h.stage_times()
