@@ -383,13 +383,7 @@ int xb_conv_stem_fwd(xb_handle *h, const void *signal, int sig_dtype, int N, int
         if (int rc = xb_conv12_im2col(h, signal, sig_dtype, N, L, s)) return rc;
     }
     xb_stage_timer tm(h, XB_ST_CONV3, s);
-    CUtensorMap tmA, tmB;
-    if (int rc = xb_make_tmap_2d(h, &tmA, h->c2, (uint64_t)N * T, XB_CONV3_K, XB_CONV3_K)) return rc;
-    if (int rc = xb_make_tmap_2d(h, &tmB, h->conv3_w, XB_FEATURES, XB_CONV3_K, XB_CONV3_K)) return rc;
-    GemmParams p;
-    p.M = N * T; p.N = XB_FEATURES; p.K = XB_CONV3_K;
-    p.bias = h->conv3_b; p.out = out_tnc; p.ldo = XB_FEATURES; p.T = T; p.NB = N;
-    return xb_gemm_launch(h, EPI_CONV3, tmA, tmB, p, s);
+    return xb_conv3_launch(h, h->c2, h->conv3_w, h->conv3_b, out_tnc, T, N, s);
 }
 
 int xb_lstm_fwd(xb_handle *h, int layer, const void *x_tnc, void *y_tnc, int T, int N, int reverse, void *stream) {

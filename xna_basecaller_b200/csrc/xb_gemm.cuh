@@ -46,5 +46,7 @@ struct BpttStep {
 };
 int xb_bptt_make_maps(xb_handle *h, BpttMaps *m, const void *dz, const void *w_hhT, const void *saved, int T, int N);
 int xb_bptt_step_launch(xb_handle *h, const BpttMaps &m, const BpttStep &p, bool dependent, cudaStream_t s);
+// conv3_gemm.cu: weight-stationary persistent GEMM of the stem's third convolution
+int xb_conv3_launch(xb_handle *h, const void *col, const void *w3, const float *bias, void *out_tnc, int T, int N, cudaStream_t s);
 int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p,
                    cudaStream_t s, bool bf16_operands = false);
