@@ -8,7 +8,8 @@
 // Epilogues
 //   EPI_F32    plain fp32 store (self test)
 //   EPI_CONV3  third Convolution of the stem as an implicit GEMM over im2col rows: + bias, swish, 16-bit store
-//              in (T, N, 768) order, which absorbs nn.Permute([2,0,1])       (bonito/nn.py:57-68,156-167)
+//              in (T, N, 768) order, which absorbs nn.Permute([2,0,1])       (bonito/nn.py:57-68,156-167); the product
+//              runs conv3_gemm.cu instead, this form remains in -DXB_EXPERIMENTS builds
 //   EPI_INPROJ LSTM input projection x_t W_ih^T + (b_ih + b_hh) for all t at once, 16-bit store (nn.py:189-193)
 //   EPI_HEAD   LinearCRFEncoder: scale * tanh(x W^T + b), blank score inserted in front of every group of
 //              n_base columns -> fp32 (T, N, C*NZ)                            (bonito/nn.py:112-133)
@@ -451,9 +452,9 @@ int xb_gemm_launch(xb_handle *h, int epi, const CUtensorMap &tmA, const CUtensor
         return launch_one<false, E>(h, tmA, tmB, p, p.M, s);      /* fp16 operands in both weight modes (xb_api.cu repack) */
     switch (epi) {
         XB_EPI_CASE(EPI_F32)
-        XB_EPI_CASE(EPI_CONV3)
         XB_EPI_CASE(EPI_CONV3_BWD)
-#ifdef XB_EXPERIMENTS      // the tile-GEMM forms of the input projection, the head and the step-wise LSTM (cross-check builds only)
+#ifdef XB_EXPERIMENTS      // the tile-GEMM forms of conv3, the input projection, the head and the step-wise LSTM (cross-check builds only)
+        XB_EPI_CASE(EPI_CONV3)
         XB_EPI_CASE(EPI_INPROJ)
         XB_EPI_CASE(EPI_HEAD)
         XB_EPI_CASE(EPI_LSTM)
