@@ -54,6 +54,18 @@ def test_conv_stem(enc5, golden):
     assert ((got.permute(1, 2, 0)[:, ::16, :] - gold).abs() / (1 + gold.abs())).max().item() < 4e-3
 
 
+@pytest.mark.parametrize('N,L', [(3, 100), (5, 165), (2, 2000), (9, 1280)])
+def test_conv_stem_shapes(enc5, N, L):
+    """conv3_gemm.cu: row blocks that cross chunk edges (T not a multiple of 32: row-copy path), chunks shorter than a
+    block (T = 20), T = 800 / 256 (TMA-store path only), a last row tile that is mostly padding."""
+    h, sd = enc5
+    x = synthetic_signal(100 + N, N, L)
+    got = h.conv_stem(x.cuda()).float().cpu()
+    ref = bo.conv_stem(sd, x).permute(2, 0, 1)
+    assert got.shape == ref.shape
+    assert ((got - ref).abs() / (1 + ref.abs())).max().item() < 4e-3
+
+
 @pytest.mark.parametrize('reverse', [True, False])
 def test_lstm_layer(enc5, reverse):
     h, sd = enc5
