@@ -247,7 +247,7 @@ int xb_conv3_launch(xb_handle *h, const void *col, const void *w3, const float *
     Conv3Params p;
     p.M = (int)M; p.T = T; p.NB = N; p.bias = bias; p.col = col; p.out = reinterpret_cast<uint16_t *>(out_tnc);
     const int ntiles = (int)((M + BM - 1) / BM);
-    int workers = 148 / GROUPS;
+    int workers = (h->num_sms > 0 ? h->num_sms : 148) / GROUPS;       // one CTA per SM
     if (workers > ntiles) workers = ntiles;
     conv3_kernel<<<GROUPS * workers, THREADS, SMEM_BYTES, s>>>(tmA, tmB, tmO, p);
     XB_LAUNCH_CHECK(h);

@@ -342,7 +342,7 @@ int transpose_to_bf16(xb_handle *h, const void *in, int R, int C, int ld_in, boo
     xb_stage_timer tm(h, XB_ST_TRAIN_TRANSPOSE, s);
     if (R % 8 == 0 && C % 8 == 0 && ld_in % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const int tiles = (R + 63) / 64, ctiles = (C + 63) / 64;
-        int slabs = (148 * 12 + ctiles - 1) / ctiles;         // ~12 CTAs per SM over the whole grid
+        int slabs = (h->num_sms * 12 + ctiles - 1) / ctiles;  // ~12 CTAs per SM over the whole grid
         if (slabs > tiles) slabs = tiles;
         dim3 grid(ctiles, slabs);
         if (colsum_out) XB_CUDA(h, cudaMemsetAsync(colsum_out, 0, (size_t)C * sizeof(float), s));
@@ -373,7 +373,7 @@ int gemm_bf16(xb_handle *h, int epi, const void *A, int M, int lda, const void *
     if (epi == EPI_F32) {
         // weight gradients: few output tiles, K = T*N deep -- slice K until the grid covers the SMs (partials added in L2)
         const int tiles = ((M + 127) / 128) * ((Nn + 127) / 128), kb = (K + 63) / 64;
-        int split = tiles >= 148 ? 1 : (2 * 148) / tiles;
+        int split = tiles >= h->num_sms ? 1 : (2 * h->num_sms) / tiles;
         if (split > kb / 8) split = kb / 8 > 0 ? kb / 8 : 1;
         if (split > 1) {
             p.split_k = split;
