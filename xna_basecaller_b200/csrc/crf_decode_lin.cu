@@ -342,6 +342,10 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
     uint64_t *empty = full + D, *cand = empty + D;
     int *scan = reinterpret_cast<int *>(cand + D);          // NTT + 1
     int8_t *lab = reinterpret_cast<int8_t *>(scan + NTT + 1);   // T
+    // POST: two staged posterior rows.  A thread owns NZ consecutive floats of a row (28-byte lane stride for NZ = 7): written
+    // straight to global memory every store instruction fills a sliver of ~28 sectors.  The row is staged here instead and
+    // leaves one step later, after the barrier the next step needs anyway, as whole 128-byte segments.
+    float *pst = POST ? reinterpret_cast<float *>(lab + ((T + 15) / 16) * 16) : nullptr;      // 2 * S
     const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
     const size_t total_rows = (size_t)T * N;
     const size_t vrow = (size_t)N * R::VP;
@@ -392,11 +396,17 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
 #pragma unroll
         for (int k = 1; k < NZ; k++) src[k] = act ? (k - 1) * L::NP + c / NB : 0;
         const size_t prow = (size_t)N * S;
-        float *pout = POST ? post_out + (size_t)n * S + c * NZ : nullptr;
+        float *prow_out = POST ? post_out + (size_t)n * S : nullptr;      // row t - 1 of this sequence
         for (int t = 0; t < T; t++) {
             const int slot = t % D;
             xbptx::mbar_wait(&full[slot], (t / D) & 1);
             compute_bar(NT);
+            if (POST && t > 0) {
+                const float *srow = pst + ((t - 1) & 1) * S;
+                for (int i = c; i < S; i += NT) prow_out[i] = srow[i];
+                prow_out += prow;
+            }
+            float *pout = POST ? pst + (t & 1) * S + c * NZ : nullptr;
             const float sc = xb_pow2_scale(red_max<W>(redm + (t & 1) * W));
             const float inv = XB_RCP(ringB[slot * R::VP + NT]);
             const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n) + c * NZ;
@@ -426,7 +436,6 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
                 }
                 am[((t + 1) & 1) * NT + c] = m;
             }
-            if (POST) pout += prow;
             const float wm = warp_max_pos(m);
             if (lane == 0) redm[((t + 1) & 1) * W + w] = wm;
             // warp arg-max with first-index ties: candidates are non-negative, so their bit patterns order like the values
@@ -445,6 +454,11 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
         }
     }
     __syncthreads();
+    if (POST && T > 0 && c < NT) {                               // the last staged row
+        const float *srow = pst + ((T - 1) & 1) * S;
+        float *dst = post_out + ((size_t)(T - 1) * N + n) * S;
+        for (int i = c; i < S; i += NT) dst[i] = srow[i];
+    }
     pack_labels<NTT>(lab, scan, T, n, labels_out, seq_out, qs_out, lens_out, abc);
 }
 
@@ -485,8 +499,9 @@ int lin_impl(xb_handle *h, const float *scores, int T, int N, int8_t *labels, in
     for (int i = 0; i < 16; i++) abc.ch[i] = h->alphabet[i];
     if (post) {
         auto k = crf_lin_viterbi_kernel<NB, SL, LIN, true>;
-        if (int rc = set_smem(h, k, sm)) return rc;
-        k<<<N, NTT, sm, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, post, abc);
+        const size_t smp = sm + 2 * sizeof(float) * L::S;        // + two staged posterior rows
+        if (int rc = set_smem(h, k, smp)) return rc;
+        k<<<N, NTT, smp, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, post, abc);
     } else {
         auto k = crf_lin_viterbi_kernel<NB, SL, LIN, false>;
         if (int rc = set_smem(h, k, sm)) return rc;
