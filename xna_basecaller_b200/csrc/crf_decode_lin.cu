@@ -345,7 +345,10 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
     // POST: two staged posterior rows.  A thread owns NZ consecutive floats of a row (28-byte lane stride for NZ = 7): written
     // straight to global memory every store instruction fills a sliver of ~28 sectors.  The row is staged here instead and
     // leaves one step later, after the barrier the next step needs anyway, as whole 128-byte segments.
-    float *pst = POST ? reinterpret_cast<float *>(lab + ((T + 15) / 16) * 16) : nullptr;      // 2 * S
+    // Only for the larger lattices (XY: 6 KB rows, 1024 sequences): on X (3 KB rows) the sweep is issue-bound and the extra
+    // shared-memory round trip costs more than the slivers (measured 1.04 against 0.82 ms at N = 512).
+    constexpr bool PSTAGE = POST && L::S >= 1024;
+    float *pst = PSTAGE ? reinterpret_cast<float *>(lab + ((T + 15) / 16) * 16) : nullptr;      // 2 * S
     const int n = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5;
     const size_t total_rows = (size_t)T * N;
     const size_t vrow = (size_t)N * R::VP;
@@ -401,12 +404,12 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
             const int slot = t % D;
             xbptx::mbar_wait(&full[slot], (t / D) & 1);
             compute_bar(NT);
-            if (POST && t > 0) {
+            if (PSTAGE && t > 0) {
                 const float *srow = pst + ((t - 1) & 1) * S;
                 for (int i = c; i < S; i += NT) prow_out[i] = srow[i];
                 prow_out += prow;
             }
-            float *pout = POST ? pst + (t & 1) * S + c * NZ : nullptr;
+            float *pout = !POST ? nullptr : PSTAGE ? pst + (t & 1) * S + c * NZ : post_out + ((size_t)t * N + n) * S + c * NZ;
             const float sc = xb_pow2_scale(red_max<W>(redm + (t & 1) * W));
             const float inv = XB_RCP(ringB[slot * R::VP + NT]);
             const float *M = ring + slot * R::ROWF + R::phase((size_t)t * N + n) + c * NZ;
@@ -454,7 +457,7 @@ crf_lin_viterbi_kernel(const float *__restrict__ scores, const float *__restrict
         }
     }
     __syncthreads();
-    if (POST && T > 0 && c < NT) {                               // the last staged row
+    if (PSTAGE && T > 0 && c < NT) {                             // the last staged row
         const float *srow = pst + ((T - 1) & 1) * S;
         float *dst = post_out + ((size_t)(T - 1) * N + n) * S;
         for (int i = c; i < S; i += NT) dst[i] = srow[i];
@@ -499,7 +502,7 @@ int lin_impl(xb_handle *h, const float *scores, int T, int N, int8_t *labels, in
     for (int i = 0; i < 16; i++) abc.ch[i] = h->alphabet[i];
     if (post) {
         auto k = crf_lin_viterbi_kernel<NB, SL, LIN, true>;
-        const size_t smp = sm + 2 * sizeof(float) * L::S;        // + two staged posterior rows
+        const size_t smp = sm + (L::S >= 1024 ? 2 * sizeof(float) * L::S : 0);        // + two staged posterior rows (see PSTAGE)
         if (int rc = set_smem(h, k, smp)) return rc;
         k<<<N, NTT, smp, s>>>(scores, alpha, beta, bmax, T, N, labels, seq, qs, lens, post, abc);
     } else {

@@ -454,21 +454,6 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
             if (lane < NC && col0 + lane < cnt)
                 *reinterpret_cast<uint4 *>(p.y + ((size_t)t * N + row0 + col0 + lane) * XB_FEATURES + j * 32 + q * 8) =
                     lds_v4(st_s + 2u * (lane * ST_PITCH));
-            if (SAVE) {       // i, f, g, o, c of the step through the same staging rows: (T, N, 5, 768) fp16
-#pragma unroll
-                for (int qn = 0; qn < 5; qn++) {
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < CELLS; i++) {
-                        const __half hv = __float2half_rn(sv[SAVE ? qn : 0][i]);
-                        sts_u16(st_s + 2u * ((8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul), *reinterpret_cast<const uint16_t *>(&hv));
-                    }
-                    __syncwarp();
-                    if (lane < NC && col0 + lane < cnt)
-                        *reinterpret_cast<uint4 *>(p.save + (((size_t)t * N + row0 + col0 + lane) * 5 + qn) * XB_FEATURES + j * 32 + q * 8) =
-                            lds_v4(st_s + 2u * (lane * ST_PITCH));
-                }
-            }
             if (ew == 0 && lane == 0) DBG(sub, 12);
             if (p.one_release) {
                 // one release per sub-batch and step instead of one per warp (MEMBAR.GPU instances of one SM appear to
@@ -485,6 +470,25 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_con
                     red_release_gpu_add(ctr, 1);              // publishes the warp's stores (cumulative over __syncwarp)
                     mbar_arrive(g_empty(sub, GB == 2 ? (s & 1) : 0));
                     if (ew == 0) DBG(sub, 13);
+                }
+            }
+            // Training forward: i, f, g, o, c of the step through the same (private, GB == 2) staging rows -> (T, N, 5, 768) fp16.
+            // AFTER h has been published: these stores feed the backward pass, not the next step, and in front of the release
+            // they sat on the step-to-step chain (five staging rounds, and the release's fence waits for every store before it).
+            if (SAVE) {
+                static_assert(!SAVE || GB == 2, "the saved-state stores reuse the staging rows after the gate buffer has been released");
+#pragma unroll
+                for (int qn = 0; qn < 5; qn++) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < CELLS; i++) {
+                        const __half hv = __float2half_rn(sv[SAVE ? qn : 0][i]);
+                        sts_u16(st_s + 2u * ((8 * (i >> 1) + 2 * gt + (i & 1)) * ST_PITCH + ul), *reinterpret_cast<const uint16_t *>(&hv));
+                    }
+                    __syncwarp();
+                    if (lane < NC && col0 + lane < cnt)
+                        *reinterpret_cast<uint4 *>(p.save + (((size_t)t * N + row0 + col0 + lane) * 5 + qn) * XB_FEATURES + j * 32 + q * 8) =
+                            lds_v4(st_s + 2u * (lane * ST_PITCH));
                 }
             }
         }
