@@ -231,6 +231,49 @@ def gpu_comparator(sd, dev, N):
             'decode_ms_scaled': dec_full, 'samples_per_s': N * CHUNK / ((enc_ms + dec_full) / 1e3)}
 
 
+def train_step_leg(dev, N):
+    """BASELINE configs[4] ("fwd_bwd"): one CTC-CRF training step of the sup@v3.3 UB X model through the plugin classes
+    (crf.Model -> Trainer.train_one_step: forward, loss, backward to all 28 parameter tensors, clip_grad_norm_(2.0), AdamW),
+    batch N x 4000 samples, targets ~U(350, 450) bases with ~9 % X spliced in.  A side measurement of the default bench run
+    (the headline metric is basecalling), device-timed, inputs resident in HBM."""
+    import numpy as np
+    from oracle import bonito_oracle as bo            # weight generator only
+    from xna_basecaller_b200.crf import Model
+    from xna_basecaller_b200.training import Trainer
+    model = Model(sup_config())
+    model.load_state_dict(bo.reference_state_dict(n_base=N_BASE, seed=25))
+    trainer = Trainer(model, dev)
+    trainer.init_optimizer(2e-3)
+    model.train()
+    x = torch.randn(N, 1, CHUNK, generator=torch.Generator().manual_seed(1234)).to(dev)
+    rs = np.random.RandomState(3)
+    lens = rs.randint(350, 451, N)
+    tg = np.zeros((N, int(lens.max())), dtype=np.int64)
+    for i, n in enumerate(lens):
+        seq = rs.randint(1, 5, n)
+        cand = np.arange(5, n - 5, 11)
+        seq[cand[rs.rand(len(cand)) < 0.99]] = 5
+        tg[i, :n] = seq
+    tg, tl = torch.from_numpy(tg).to(dev), torch.from_numpy(lens).to(dev)
+    for _ in range(2):
+        losses, _ = trainer.train_one_step((x, tg, tl))
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        losses, _ = trainer.train_one_step((x, tg, tl))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    out = {'config': 'configs[4]: training step (fwd + CTC-CRF loss + bwd + clip + AdamW), batch %d x %d samples, fp16 forward '
+                     'operands, bf16 gradient transport, fp32 accumulation and master weights' % (N, CHUNK),
+           'ms_per_step': ms, 'samples_per_s': N * CHUNK / ms * 1e3, 'loss': float(losses['loss'])}
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def sup_config():
     return {'global_norm': {'state_len': STATE_LEN}, 'input': {'features': 1}, 'labels': {'labels': list(ALPHABET)},
             'model': {'package': 'xna_basecaller_b200.crf'},
@@ -379,6 +422,7 @@ def main():
     ap.add_argument('--head-gain', type=float, default=None, help='skip the head-gain calibration and use this gain')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-comparator', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -547,6 +591,11 @@ def main():
                 line['gpu_comparator'] = gpu_comparator(sd, dev, N)
             except Exception as e:                                    # a baseline leg must not take the bench line down
                 line['gpu_comparator'] = {'unavailable': repr(e)[:200]}
+        if world == 1 and not args.no_train_step:
+            try:
+                line['train_step'] = train_step_leg(dev, N)
+            except Exception as e:                                    # a side leg must not take the bench line down
+                line['train_step'] = {'unavailable': repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_chunks = 64                             # = BASELINE.json configs[0]
