@@ -198,3 +198,92 @@ def test_lr_schedules_match_reference_golden():
             opt.step()
             sch.step()
         assert [got[i] for i in (0, 1, 50, 99, 100, 249, 250, 499, 500, 749)] == want
+
+
+# ----------------------------------------------------------------------------- training data path
+def _write_ctc_dir(path, n, L=200, Lmax=30, seed=0, indices=None):
+    import os
+    rs = np.random.RandomState(seed)
+    os.makedirs(path, exist_ok=True)
+    chunks = rs.randn(n, L).astype(np.float16)
+    lengths = rs.randint(5, Lmax + 1, n).astype(np.uint16)
+    targets = np.zeros((n, Lmax), dtype=np.uint8)
+    for i, k in enumerate(lengths):
+        targets[i, :k] = rs.randint(1, 7, k)
+    np.save(os.path.join(path, 'chunks.npy'), chunks)
+    np.save(os.path.join(path, 'references.npy'), targets)
+    np.save(os.path.join(path, 'reference_lengths.npy'), lengths)
+    if indices is not None:
+        np.save(os.path.join(path, 'indices.npy'), np.asarray(indices))
+    return chunks, targets, lengths
+
+
+def test_load_numpy_datasets_limit_and_indices(tmp_path):
+    """bonito/data.py:129-163: plain directory with `limit`; indices.npy sub-sampling (out-of-range indices dropped first,
+    then `limit`)."""
+    from xna_basecaller_b200 import data
+    d = str(tmp_path / 'plain')
+    chunks, targets, lengths = _write_ctc_dir(d, 50)
+    c, t, l = data.load_numpy_datasets(limit=20, directory=d)
+    assert c.shape == (20, 200) and np.array_equal(c, chunks[:20]) and np.array_equal(t, targets[:20]) and np.array_equal(l, lengths[:20])
+    c, t, l = data.load_numpy_datasets(directory=d)
+    assert len(l) == 50
+    d2 = str(tmp_path / 'indexed')
+    chunks, targets, lengths = _write_ctc_dir(d2, 40, indices=[7, 3, 99, 12, 5])
+    c, t, l = data.load_numpy_datasets(limit=3, directory=d2)
+    assert np.array_equal(c, chunks[[7, 3, 12]]) and np.array_equal(l, lengths[[7, 3, 12]])
+
+
+def test_load_numpy_split_and_items(tmp_path, capsys):
+    """data.py:100-126: 97 % / 3 % split without a validation directory, validation/ used when present; item dtypes of
+    ChunkDataSet (data.py:53-57); augmentation arguments are refused, not ignored."""
+    from xna_basecaller_b200 import data
+    d = str(tmp_path / 'set')
+    chunks, targets, lengths = _write_ctc_dir(d, 100)
+    tr, va = data.load_numpy(None, d)
+    assert 'splitting training set' in capsys.readouterr().out
+    assert len(tr['dataset']) == 97 and len(va['dataset']) == 3 and tr['shuffle'] and not va['shuffle']
+    chunk, target, length = va['dataset'][1]
+    assert chunk.shape == (1, 200) and chunk.dtype == np.float32 and target.dtype == np.int64 and length.dtype == np.int64
+    assert np.array_equal(chunk[0], chunks[98].astype(np.float32)) and int(length) == int(lengths[98])
+    _write_ctc_dir(str(tmp_path / 'set' / 'validation'), 11, seed=5)
+    tr, va = data.load_numpy(60, d)
+    assert len(tr['dataset']) == 60 and len(va['dataset']) == 11
+    with pytest.raises(NotImplementedError):
+        data.load_numpy(None, d, spike_kwargs={'prop_ubs': 0.09})
+
+
+def test_device_chunk_loader_covers_every_item_once(tmp_path):
+    """DeviceChunkLoader (logic checked on the CPU device): every item exactly once per pass, short last batch, reproducible
+    shuffles that differ between passes, the Y -> X replacement of data.py:82-83."""
+    from xna_basecaller_b200 import data
+    d = str(tmp_path / 'set')
+    chunks, targets, lengths = _write_ctc_dir(d, 37)
+    ds = data.ChunkDataSet(*data.load_numpy_datasets(directory=d))
+    ds.replace_6_letter = True
+    ld = data.DeviceChunkLoader(ds, batch_size=8, shuffle=True, device='cpu', seed=3)
+    assert len(ld) == 5 and len(ld.sampler) == 37
+    passes = []
+    for _ in range(2):
+        seen = []
+        for x, t, l in ld:
+            assert x.dtype == torch.float32 and x.shape[1:] == (1, 200) and t.dtype == torch.int64 and l.dtype == torch.int64
+            assert not (t == 6).any()
+            for row, ln in zip(x[:, 0], l):          # identify the item by its signal
+                i = int(np.flatnonzero((chunks.astype(np.float32) == row.numpy()).all(1))[0])
+                assert int(ln) == int(lengths[i])
+                seen.append(i)
+        assert sorted(seen) == list(range(37))
+        passes.append(seen)
+    assert passes[0] != passes[1] and passes[0] != list(range(37))
+    again = data.DeviceChunkLoader(ds, batch_size=8, shuffle=True, device='cpu', seed=3)
+    assert [int(l[0]) for _, _, l in again] == [int(lengths[passes[0][k]]) for k in range(0, 37, 8)]
+    plain = data.DeviceChunkLoader(ds, batch_size=16, shuffle=False, device='cpu')
+    assert torch.equal(torch.cat([l for _, _, l in plain]), torch.from_numpy(lengths.astype(np.int64)))
+    # batch_multiple=8 (what the training step of this package needs): 37 items -> batches of 16, 16 and nothing left over
+    m8 = data.DeviceChunkLoader(ds, batch_size=16, shuffle=True, device='cpu', seed=4, batch_multiple=8)
+    assert len(m8) == 2 and [x.shape[0] for x, _, _ in m8] == [16, 16]
+    m8b = data.DeviceChunkLoader(ds, batch_size=24, shuffle=False, device='cpu', batch_multiple=8)
+    assert [x.shape[0] for x, _, _ in m8b] == [24, 8]
+    with pytest.raises(ValueError):
+        data.DeviceChunkLoader(ds, batch_size=12, device='cpu', batch_multiple=8)

@@ -131,3 +131,44 @@ def test_trainer_train_one_step_through_the_plugin():
         first = losses['loss'] if first is None else first
     assert losses['loss'] < first
     print('loss %.4f -> %.4f in 6 steps, last grad norm %.3f' % (first, losses['loss'], grad_norm))
+
+
+def test_device_chunk_loader_feeds_the_trainer(tmp_path):
+    """Training data path (bonito/data.py): a ctc-data directory -> load_numpy -> DeviceChunkLoader (data set resident in
+    HBM, batches gathered on the device) -> Trainer.train_one_step.  Passes over the set lower the loss."""
+    from make_golden import synthetic_targets
+    from xna_basecaller_b200 import data, util
+    from xna_basecaller_b200.training import Trainer
+    N, L = 16, 600
+    x = synthetic_signal(61, N, L)
+    tg, tl = synthetic_targets(9, N, 5, 40, 60)
+    d = str(tmp_path)
+    np.save(d + '/chunks.npy', x[:, 0].numpy().astype(np.float16))
+    np.save(d + '/references.npy', tg.numpy().astype(np.uint8))
+    np.save(d + '/reference_lengths.npy', tl.numpy().astype(np.uint16))
+    np.save(d + '/indices.npy', np.arange(N))
+    train_kwargs, _ = data.load_numpy(None, d)                     # 97 % / 3 % split: 15 + 1 chunks
+    # unshuffled here, so that every pass trains on the same 8 chunks and the loss must fall (the 7 left-over chunks of the
+    # 15 are cut off by batch_multiple=8; shuffled, others would be left over in the next pass)
+    loader = data.DeviceChunkLoader(batch_size=8, device='cuda', batch_multiple=8, **dict(train_kwargs, shuffle=False))
+    assert len(loader.sampler) == 15 and len(loader) == 1
+    cfg = {'global_norm': {'state_len': 3}, 'input': {'features': 1}, 'labels': {'labels': ALPHABETS[5]},
+           'model': {'package': 'xna_basecaller_b200.crf'},
+           'encoder': {'stride': 5, 'activation': 'swish', 'features': 768, 'winlen': 19, 'scale': 5.0,
+                       'rnn_type': 'lstm', 'blank_score': 2.0}}
+    model = util.load_symbol(cfg, 'Model')(cfg)
+    model.load_state_dict(bo.reference_state_dict(n_base=5, seed=12, **REF_SCALE))
+    trainer = Trainer(model, 'cuda', train_loader=loader)
+    trainer.init_optimizer(1e-3)
+    per_pass = []
+    for _ in range(6):
+        seen, total = 0, 0.0
+        for batch in loader:
+            assert batch[0].is_cuda and batch[0].shape[1:] == (1, L)
+            losses, grad_norm = trainer.train_one_step(batch)
+            assert np.isfinite(losses['loss']) and np.isfinite(grad_norm)
+            seen += batch[0].shape[0]
+            total += losses['loss'] * batch[0].shape[0]
+        assert seen == 8
+        per_pass.append(total / seen)
+    assert per_pass[-1] < per_pass[0], per_pass

@@ -430,7 +430,11 @@ int xb_encoder_fwd_train(xb_handle *h, const void *signal, int sig_dtype, int N,
     XB_REQUIRE(h, (h->loaded & 127) == 127, "weights have not been loaded (xb_load_weights)");
     const int T = L / XB_STRIDE;
     XB_REQUIRE(h, T <= h->max_T && N <= h->max_N && N > 0, "T=%d N=%d exceed the handle capacity", T, N);
-    XB_REQUIRE(h, N % 8 == 0, "the training path needs a batch that is a multiple of 8 (16-byte aligned time-shifted views); got %d", N);
+    // N % 8: the K = T*N contractions read K-major transposed copies through TMA -- their row pitch (T*N 16-bit elements)
+    // must be a multiple of 16 bytes, and so must the byte offset of dW_hh's time shift (N elements along such a row:
+    // an unaligned box start raises an illegal-instruction error, measured with N = 7)
+    XB_REQUIRE(h, N % 8 == 0, "the training path needs a batch that is a multiple of 8 (16-byte TMA alignment of the time-shifted "
+                              "operand views); got %d", N);
     XB_CUDA(h, cudaSetDevice(h->device));
     if (int rc = train_ws(h, N, T)) return rc;
     xb_train_ws *w = h->train;
